@@ -1,0 +1,104 @@
+"""render_viewpoints with the reference's two signatures (run.py:66-171, run_sr.py:74-182).
+
+Differences that do not change results: rays are generated on the device (k4_make_rays), the whole
+frame is ONE fused launch instead of 8192-ray chunks (the chunk loop only bounds the reference's
+intermediate memory, run_sr.py:121-124), and metrics that need packages absent from this image
+(SSIM via scipy is fine, LPIPS is not) raise if requested.
+"""
+import numpy as np
+import torch
+
+from . import dvgo
+
+
+@torch.no_grad()
+def _render_frames(model, render_poses, HW, Ks, ndc, render_kwargs, render_factor, flip_x, flip_y):
+    if render_factor != 0:
+        HW = np.copy(HW)
+        Ks = np.copy(Ks)
+        HW = (HW / render_factor).astype(int)
+        Ks[:, :2, :3] /= render_factor
+    frames = []
+    for i, c2w in enumerate(render_poses):
+        H, W = int(HW[i][0]), int(HW[i][1])
+        K = Ks[i]
+        rays_o, rays_d, viewdirs = dvgo.get_rays_of_a_view(
+            H, W, K, torch.as_tensor(np.asarray(c2w), dtype=torch.float32), ndc,
+            inverse_y=render_kwargs['inverse_y'], flip_x=flip_x, flip_y=flip_y)
+        ret = model.render_rays(rays_o.view(-1, 3), rays_d.view(-1, 3), viewdirs.view(-1, 3),
+                                render_kwargs, image_hw=(H, W))
+        frames.append({
+            'rgb_marched': ret['rgb_marched'].view(H, W, 3),
+            'rgb_feature': ret['rgb_marched'].view(H, W, 3),
+            'depth': ret['depth'].view(H, W, 1) if 'depth' in ret else None,
+            'alphainv_last': ret['alphainv_last'].view(H, W, 1),
+            'viewdirs': viewdirs.view(-1, 3),
+        })
+    return frames
+
+
+def _post(rgbs, depths, bgmaps, render_video_flipy, render_video_rot90):
+    if render_video_flipy:
+        for i in range(len(rgbs)):
+            rgbs[i] = np.flip(rgbs[i], axis=0); depths[i] = np.flip(depths[i], axis=0); bgmaps[i] = np.flip(bgmaps[i], axis=0)
+    if render_video_rot90 != 0:
+        for i in range(len(rgbs)):
+            rgbs[i] = np.rot90(rgbs[i], k=render_video_rot90, axes=(0, 1))
+            depths[i] = np.rot90(depths[i], k=render_video_rot90, axes=(0, 1))
+            bgmaps[i] = np.rot90(bgmaps[i], k=render_video_rot90, axes=(0, 1))
+
+
+@torch.no_grad()
+def render_viewpoints(model, render_poses, HW, Ks, ndc, render_kwargs,
+                      gt_imgs=None, savedir=None, dump_images=False,
+                      render_factor=0, render_video_flipy=False, render_video_rot90=0,
+                      eval_ssim=False, eval_lpips_alex=False, eval_lpips_vgg=False,
+                      flip_x=None, flip_y=None):
+    """run.py:66-171 contract: returns ``(rgbs, depths, bgmaps, psnrs, ssims, lpips_vgg)``.
+
+    The reference reads ``cfg.data.flip_x/flip_y`` from a module global (run.py:96); here they come
+    from ``render_kwargs`` unless passed explicitly."""
+    assert len(render_poses) == len(HW) and len(HW) == len(Ks)
+    if eval_lpips_alex or eval_lpips_vgg or eval_ssim:
+        raise NotImplementedError('SSIM/LPIPS evaluation is outside the rendering hot path')
+    flip_x = render_kwargs.get('flip_x', False) if flip_x is None else flip_x
+    flip_y = render_kwargs.get('flip_y', False) if flip_y is None else flip_y
+    frames = _render_frames(model, render_poses, HW, Ks, ndc, render_kwargs, render_factor, flip_x, flip_y)
+    rgbs, depths, bgmaps, psnrs = [], [], [], []
+    for i, f in enumerate(frames):
+        rgb = f['rgb_marched'].clamp(0, 1).cpu().numpy()
+        rgbs.append(rgb)
+        depths.append(f['depth'].cpu().numpy() if f['depth'] is not None else None)
+        bgmaps.append(f['alphainv_last'].cpu().numpy())
+        if gt_imgs is not None and render_factor == 0:
+            psnrs.append(-10. * np.log10(np.mean(np.square(rgb - gt_imgs[i]))))
+    _post(rgbs, depths, bgmaps, render_video_flipy, render_video_rot90)
+    return np.array(rgbs), np.array(depths), np.array(bgmaps), psnrs, [], []
+
+
+@torch.no_grad()
+def render_viewpoints_sr(model, render_poses, HW, Ks, ndc, render_kwargs,
+                         gt_imgs=None, savedir=None, dump_images=False,
+                         render_factor=0, render_video_flipy=False, render_video_rot90=0,
+                         eval_ssim=False, eval_lpips_alex=False, eval_lpips_vgg=False, global_step=0,
+                         arr_index=None, img_enc=None, flip_x=None, flip_y=None):
+    """run_sr.py:74-182 contract: returns ``(rgbs, depths, bgmaps, psnrs, viewdirs_all, rgb_features)``
+    where ``rgb_features`` is the UNclamped render fed to the VC-Decoder (run_sr.py:131)."""
+    assert len(render_poses) == len(HW) and len(HW) == len(Ks)
+    if arr_index is not None or img_enc is not None:
+        raise NotImplementedError('img_enc conditioning needs lib/img_encoder, which the reference does not ship')
+    flip_x = render_kwargs.get('flip_x', False) if flip_x is None else flip_x
+    flip_y = render_kwargs.get('flip_y', False) if flip_y is None else flip_y
+    frames = _render_frames(model, render_poses, HW, Ks, ndc, render_kwargs, render_factor, flip_x, flip_y)
+    rgbs, rgb_features, depths, bgmaps, psnrs, viewdirs_all = [], [], [], [], [], []
+    for i, f in enumerate(frames):
+        rgb = f['rgb_marched'].clamp(0, 1).cpu().numpy()
+        rgbs.append(rgb)
+        rgb_features.append(f['rgb_feature'].cpu().numpy())
+        depths.append(f['depth'].cpu().numpy())
+        bgmaps.append(f['alphainv_last'].cpu().numpy())
+        viewdirs_all.append(f['viewdirs'])
+        if gt_imgs is not None and render_factor == 0:
+            psnrs.append(-10. * np.log10(np.mean(np.square(rgb - gt_imgs[i]))))
+    _post(rgbs, depths, bgmaps, render_video_flipy, render_video_rot90)
+    return np.array(rgbs), np.array(depths), np.array(bgmaps), psnrs, viewdirs_all, np.array(rgb_features)

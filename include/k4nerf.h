@@ -1,0 +1,157 @@
+/*
+ * k4nerf.h -- C ABI of libk4nerf.so, the B200 (sm_100a) implementation of the 4K-NeRF rendering
+ * hot path.  This header is the drop-in boundary: plain pointers and sizes,
+ * no torch types.  The reference has no C ABI of its own; every entry point below names the
+ * reference interface it replaces (file:line under /root/reference).  The Python host mirror of
+ * the reference API (k4nerf.dvgo.DirectVoxGO etc.) is a thin ctypes caller of these functions;
+ * INTEGRATION.md shows the binding a reference maintainer would add.
+ *
+ * Conventions
+ *  - every function returns K4_OK (0) or a negative k4_status; nothing throws, nothing exits;
+ *  - all pointers named d_* / inside descriptors are DEVICE pointers on the current device unless
+ *    the name says host (h_*); fp32 unless stated;
+ *  - the caller allocates and owns all outputs and the workspace; no hidden allocation, no hidden
+ *    host synchronisation on the render calls (the reference syncs twice per call:
+ *    lib/cuda/render_utils_kernel.cu:212 and :635);
+ *  - all work is enqueued on the given stream (pass torch.cuda.current_stream().cuda_stream);
+ *  - re-entrant across streams; a k4_scene is immutable after creation.
+ */
+#ifndef K4NERF_H_
+#define K4NERF_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define K4_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define K4_API __attribute__((visibility("default")))
+#else
+#define K4_API
+#endif
+
+typedef enum k4_status {
+    K4_OK = 0,
+    K4_ERR_INVALID_ARG = -1,   /* NULL pointer, bad shape, bad enum                     */
+    K4_ERR_UNSUPPORTED = -2,   /* valid in the reference but not built here (see DESIGN) */
+    K4_ERR_CUDA = -3,          /* a CUDA runtime call failed; see k4_last_cuda_error()   */
+    K4_ERR_WORKSPACE = -4,     /* workspace NULL or smaller than k4_render_workspace_bytes */
+    K4_ERR_NO_DEVICE = -5      /* no sm_100 device / library built for another arch      */
+} k4_status;
+
+typedef void* k4_stream_t;                 /* cudaStream_t */
+typedef struct k4_scene k4_scene;          /* opaque: device-resident, repacked scene     */
+typedef struct k4_srnet k4_srnet;          /* opaque: device-resident VC-Decoder weights  */
+
+enum { K4_KIND_DVGO = 0,                   /* DirectVoxGO,  lib/dvgo.py:23-448   */
+       K4_KIND_DMPIGO = 1 };               /* DirectMPIGO,  lib/dmpigo.py:18-427 */
+
+enum { K4_MLP_FP32 = 0,                    /* fp32 FFMA, sequential accumulation (exact mode)   */
+       K4_MLP_F16 = 1,                     /* tensor cores, fp16 operands, fp32 accumulate       */
+       K4_MLP_F16X3 = 2,                   /* tensor cores, error-compensated 3-term fp16 split  */
+       K4_MLP_TCGEN05 = 3 };               /* tcgen05 + TMEM, fp16 operands (CTA-wide batches)   */
+
+#define K4_MAX_MLP_LAYERS 8
+
+/*
+ * Scene description = the tensors of a reference checkpoint's `model_state_dict` plus the derived
+ * scalars its constructor computes (SURVEY.md section 5 "Checkpoint"):
+ *   density.grid [1,1,X,Y,Z], k0.grid [1,C,X,Y,Z] (planar, z fastest: lib/grid.py:115),
+ *   mask_cache.mask [mX,mY,mZ] bool + xyz2ijk_scale/shift (lib/grid.py:290-293),
+ *   act_shift (DVGO scalar lib/dvgo.py:46 | MPI grid [1,1,1,1,D] lib/dmpigo.py:48-58),
+ *   rgbnet.{0,1.0,...}.{weight,bias} (lib/dvgo.py:116-124; weight [out,in] row major).
+ * k4_scene_create copies/repacks everything it needs; the caller may free its tensors afterwards.
+ */
+typedef struct k4_scene_desc {
+    int32_t kind;                 /* K4_KIND_*                                                  */
+    int32_t world_size[3];        /* X, Y, Z                                                    */
+    int32_t k0_dim;               /* C (3 when rgbnet_depth == 0)                               */
+    int32_t mask_size[3];         /* mX, mY, mZ                                                 */
+    float xyz_min[3];
+    float xyz_max[3];
+    float xyz2ijk_scale[3];
+    float xyz2ijk_shift[3];
+    float act_shift;              /* DVGO: density bias (lib/dvgo.py:46); MPI: ignored          */
+    float voxel_size;             /* DVGO: lib/dvgo.py:155; MPI: ignored                        */
+    float voxel_size_ratio;       /* lib/dvgo.py:158 | lib/dmpigo.py:164                        */
+    float fast_color_thres;       /* lib/dvgo.py:38                                             */
+    int32_t max_world_size;       /* DVGO: world_size.max() (depth normalisation, dvgo.py:311)  */
+    int32_t mpi_depth;            /* MPI: number of planes (lib/dmpigo.py:159)                  */
+    int32_t rgbnet_depth;         /* number of Linear layers; 0 = no MLP, rgb = sigmoid(k0)     */
+    int32_t rgbnet_width;
+    int32_t rgbnet_direct;        /* DVGO only (lib/dvgo.py:382-386,409-412)                    */
+    int32_t viewbase_pe;          /* number of view-direction frequencies                       */
+    int32_t spatial_pe;           /* MPI only: number of positional frequencies                 */
+    int32_t reserved0;
+    const float* d_density;       /* [X*Y*Z]                                                    */
+    const float* d_k0;            /* [C*X*Y*Z] planar, reference layout                         */
+    const uint8_t* d_mask;        /* [mX*mY*mZ] bytes, non-zero = occupied                      */
+    const float* d_act_shift_grid;/* MPI: [mpi_depth]; DVGO: NULL                               */
+    const float* d_rgbnet_weight[K4_MAX_MLP_LAYERS]; /* [out,in] row major                      */
+    const float* d_rgbnet_bias[K4_MAX_MLP_LAYERS];   /* [out]                                   */
+} k4_scene_desc;
+
+/* render_kwargs of the reference forward (run_sr.py:1311-1320; lib/dvgo.py:327) + kernel knobs. */
+typedef struct k4_render_args {
+    float near_;                  /* render_kwargs['near']                                      */
+    float far_;                   /* render_kwargs['far'] (DVGO forces 1e9, lib/dvgo.py:307)    */
+    float stepsize;               /* render_kwargs['stepsize']                                  */
+    float bg;                     /* render_kwargs['bg']                                        */
+    int32_t render_depth;         /* render_kwargs['render_depth']                              */
+    int32_t mlp_mode;             /* K4_MLP_*                                                   */
+    int32_t image_w;              /* >0: rays are a row-major HxW image -> 8x4 pixel tiles/warp */
+    int32_t image_h;
+} k4_render_args;
+
+typedef struct k4_render_out {
+    float* d_rgb_marched;         /* [N,3]  == rgb_feature (aliased in the reference, dvgo.py:425-427) */
+    float* d_depth;               /* [N] or NULL                                                */
+    float* d_alphainv_last;       /* [N]                                                        */
+    int32_t* d_ray_stats;         /* optional [N,4]: N_steps, S_m, S_d, S_c per ray (parity)    */
+    float* d_t_minmax;            /* optional [N,2]: t_min, t_max per ray (parity)              */
+    unsigned long long* d_counters; /* optional [4]: total S_m, S_d, S_c, MLP batches           */
+} k4_render_out;
+
+K4_API int k4_abi_version(void);
+K4_API const char* k4_status_string(int status);
+K4_API const char* k4_last_cuda_error(void);       /* thread-local text of the last CUDA failure */
+K4_API int k4_device_check(void);                  /* K4_OK iff the current device is sm_100     */
+
+/* Replaces: utils.load_model -> model.to(device) (lib/utils.py:62-66) for the marcher's tensors. */
+K4_API int k4_scene_create(const k4_scene_desc* desc, k4_stream_t stream, k4_scene** out_scene);
+K4_API int k4_scene_destroy(k4_scene* scene);
+K4_API size_t k4_scene_device_bytes(const k4_scene* scene);
+
+/* Scratch needed by k4_render_rays for n_rays (a few bytes of scheduler state). */
+K4_API size_t k4_render_workspace_bytes(const k4_scene* scene, int64_t n_rays);
+
+/*
+ * Replaces: DirectVoxGO.forward (lib/dvgo.py:327-448) / DirectMPIGO.forward (lib/dmpigo.py:292-427)
+ * at inference, i.e. the whole chain sample_pts_on_rays -> maskcache_lookup -> grid_sample ->
+ * raw2alpha -> alpha2weight -> grid_sample -> rgbnet -> segment_coo in ONE launch.
+ * d_rays_o/d_rays_d/d_viewdirs: [N,3] contiguous fp32 (the reference CHECK_CONTIGUOUS contract,
+ * lib/cuda/render_utils.cpp:46-48).  Any N >= 0.
+ */
+K4_API int k4_render_rays(const k4_scene* scene, const k4_render_args* args,
+                   const float* d_rays_o, const float* d_rays_d, const float* d_viewdirs,
+                   int64_t n_rays, const k4_render_out* out,
+                   void* d_workspace, size_t workspace_bytes, k4_stream_t stream);
+
+/*
+ * Replaces: get_rays_of_a_view (lib/dvgo.py:516-582) feeding the chunk loop of render_viewpoints
+ * (run_sr.py:99-128): pixel-centre rays of an HxW pinhole view generated on the device.
+ * h_K: 9 floats row major, h_c2w: 12 floats (3x4) row major, both HOST pointers.
+ * d_rays_o/d_rays_d/d_viewdirs: [H*W,3] outputs.
+ */
+K4_API int k4_make_rays(const float* h_K, const float* h_c2w, int32_t H, int32_t W, int32_t ndc,
+                 int32_t inverse_y, int32_t flip_x, int32_t flip_y,
+                 float* d_rays_o, float* d_rays_d, float* d_viewdirs, k4_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* K4NERF_H_ */

@@ -1,0 +1,70 @@
+"""Build the UNMODIFIED-SEMANTICS reference CUDA extension into oracle/_ref/ (test infrastructure only).
+
+This is checker infrastructure, not product code: only tests/, __graft_entry__.smoke() and
+bench.py's reference/cpu_baseline legs may load what this script produces.
+
+What it does
+------------
+The reference's ray-march ops live in /root/reference/lib/cuda/render_utils.cpp and
+render_utils_kernel.cu (13 pybind functions, render_utils.cpp:170-184).  They do not compile
+against torch 2.11 as shipped: the 13 `AT_DISPATCH_FLOATING_TYPES(x.type(), ...)` sites in
+render_utils_kernel.cu need a `ScalarType`, and `.type()` returns `DeprecatedTypeProperties`
+(SURVEY.md section 0).  This recipe
+
+  1. copies the two source files from where they lie under /root/reference into a scratch
+     directory under /tmp (never into the repository),
+  2. rewrites `.type()` -> `.scalar_type()` inside the AT_DISPATCH calls (a mechanical,
+     semantics-preserving token patch; nothing else is touched),
+  3. compiles them for sm_100a with torch.utils.cpp_extension (no fast-math, nvcc defaults,
+     i.e. the flags the reference's own JIT `load(...)` call would use, lib/dvgo.py:14-19),
+  4. leaves ONLY the built shared object in oracle/_ref/render_utils_cuda.so.
+
+oracle/_ref/ is git-ignored (binary, derived from reference sources) but travels to the GPU box
+with the gpurun snapshot, where tests use it as the GPU-side reference for the op-level
+restatement in oracle/render_utils_ref.c.  /root/reference does not exist on the GPU box, so this
+script is a no-op there (it keeps whatever prebuilt .so travelled with the snapshot).
+"""
+import os
+import re
+import shutil
+import sys
+import tempfile
+
+REF = '/root/reference/lib/cuda'
+HERE = os.path.dirname(os.path.abspath(__file__))
+OUT_DIR = os.path.join(HERE, '_ref')
+OUT_SO = os.path.join(OUT_DIR, 'render_utils_cuda.so')
+
+
+def build(force=False, verbose=False):
+    if not os.path.isdir(REF):
+        return OUT_SO if os.path.exists(OUT_SO) else None
+    if os.path.exists(OUT_SO) and not force:
+        return OUT_SO
+    os.makedirs(OUT_DIR, exist_ok=True)
+    work = tempfile.mkdtemp(prefix='k4_refbuild_')
+    srcs = []
+    for name in ('render_utils.cpp', 'render_utils_kernel.cu'):
+        with open(os.path.join(REF, name)) as f:
+            text = f.read()
+        text = re.sub(r'(AT_DISPATCH_FLOATING_TYPES\(\s*[A-Za-z_0-9]+)\.type\(\)', r'\1.scalar_type()', text)
+        dst = os.path.join(work, name)
+        with open(dst, 'w') as f:
+            f.write(text)
+        srcs.append(dst)
+    os.environ.setdefault('TORCH_CUDA_ARCH_LIST', '10.0a')
+    os.environ.setdefault('MAX_JOBS', str(os.cpu_count() or 4))
+    from torch.utils.cpp_extension import load
+    bdir = os.path.join(work, 'build')
+    os.makedirs(bdir)
+    load(name='render_utils_cuda', sources=srcs, build_directory=bdir, verbose=verbose,
+         is_python_module=False)
+    built = os.path.join(bdir, 'render_utils_cuda.so')
+    shutil.copyfile(built, OUT_SO)
+    shutil.rmtree(work, ignore_errors=True)
+    return OUT_SO
+
+
+if __name__ == '__main__':
+    p = build(force='--force' in sys.argv, verbose=True)
+    print('oracle/_ref:', p)

@@ -1,0 +1,86 @@
+"""CPU: host-side mirror of the reference API -- constructor arithmetic, state-dict layout,
+checkpoint round trip, error behaviour (no compute calls, no GPU)."""
+import os
+import tempfile
+
+import pytest
+import torch
+
+import k4nerf
+from oracle import pipeline
+from helpers import make_state, model_from_state
+
+
+def test_dvgo_constructor_matches_oracle_arithmetic():
+    st = pipeline.dvgo_state([-1.1, -0.9, -1.0], [1.0, 1.2, 0.8], num_voxels=50 ** 3, num_voxels_base=40 ** 3,
+                             alpha_init=1e-2, fast_color_thres=1e-4, rgbnet_dim=12, rgbnet_direct=True)
+    m = k4nerf.DirectVoxGO([-1.1, -0.9, -1.0], [1.0, 1.2, 0.8], num_voxels=50 ** 3, num_voxels_base=40 ** 3,
+                           alpha_init=1e-2, fast_color_thres=1e-4, rgbnet_dim=12, rgbnet_direct=True)
+    assert m.world_size.tolist() == st['world_size'].tolist()
+    assert torch.equal(m.voxel_size, st['voxel_size'])
+    assert torch.equal(m.voxel_size_ratio, st['voxel_size_ratio'])
+    assert torch.equal(m.act_shift, st['act_shift'])
+    assert torch.equal(m.mask_cache.xyz2ijk_scale, st['mask_cache']['xyz2ijk_scale'])
+    assert torch.equal(m.mask_cache.xyz2ijk_shift, st['mask_cache']['xyz2ijk_shift'])
+    assert m.dim0 == st['dim0'] == 39
+    assert list(m.density.grid.shape) == list(st['density'].shape)
+    assert list(m.k0.grid.shape) == list(st['k0'].shape)
+
+
+def test_dmpigo_constructor_matches_oracle_arithmetic():
+    args = dict(num_voxels=96 * 96 * 64, mpi_depth=64, fast_color_thres=1 / 64 / 5, rgbnet_dim=9, rgbnet_width=64)
+    st = pipeline.dmpigo_state([-1.5, -1.67, -1], [1.5, 1.67, 1], **args)
+    m = k4nerf.DirectMPIGO([-1.5, -1.67, -1], [1.5, 1.67, 1], act_type='relu', mode_type='mlp', **args)
+    assert m.world_size.tolist() == st['world_size'].tolist()
+    assert m.voxel_size_ratio == st['voxel_size_ratio']
+    assert torch.equal(m.act_shift.grid, st['act_shift_grid'])
+    assert m.dim0 == st['dim0'] == 15
+
+
+def test_state_dict_keys_follow_reference_module_tree():
+    m = k4nerf.DirectVoxGO([-1, -1, -1], [1, 1, 1], num_voxels=16 ** 3, num_voxels_base=16 ** 3, alpha_init=1e-2,
+                           fast_color_thres=1e-4, rgbnet_dim=12, rgbnet_direct=True, rgbnet_depth=3)
+    keys = set(m.state_dict())
+    # lib/dvgo.py:116-123: Sequential(Linear, ReLU, Sequential(Linear, ReLU), Linear)
+    for k in ('density.grid', 'k0.grid', 'mask_cache.mask', 'mask_cache.xyz2ijk_scale', 'mask_cache.xyz2ijk_shift',
+              'act_shift', 'xyz_min', 'xyz_max', 'viewfreq', 'rgbnet.0.weight', 'rgbnet.2.0.weight', 'rgbnet.3.bias',
+              'density.xyz_min', 'k0.xyz_max'):
+        assert k in keys, k
+
+
+def test_checkpoint_round_trip_reference_layout():
+    st = make_state('cfgA', res=12)
+    m = model_from_state(st)
+    with tempfile.TemporaryDirectory() as d:
+        path = os.path.join(d, 'fine_last.tar')
+        # the reference's checkpoint layout, run_sr.py:1163-1168
+        torch.save({'global_step': 7, 'model_kwargs': m.get_kwargs(), 'model_state_dict': m.state_dict(),
+                    'optimizer_state_dict': {}}, path)
+        m2 = k4nerf.utils.load_model(k4nerf.DirectVoxGO, path)
+    for k, v in m.state_dict().items():
+        assert torch.equal(v, m2.state_dict()[k]), k
+
+
+def test_load_state_dict_adopts_checkpoint_grid_shapes():
+    m = k4nerf.DirectVoxGO([-1, -1, -1], [1, 1, 1], num_voxels=16 ** 3, num_voxels_base=16 ** 3, alpha_init=1e-2,
+                           fast_color_thres=1e-4, rgbnet_dim=12, rgbnet_direct=True)
+    sd = m.state_dict()
+    sd['density.grid'] = torch.zeros(1, 1, 15, 17, 16)
+    sd['k0.grid'] = torch.zeros(1, 12, 15, 17, 16)
+    sd['mask_cache.mask'] = torch.ones(15, 17, 16, dtype=torch.bool)
+    m.load_state_dict(sd)
+    assert list(m.k0.grid.shape) == [1, 12, 15, 17, 16]
+
+
+def test_cpu_tensors_raise_like_check_cuda():
+    st = make_state('cfgA', res=8)
+    m = model_from_state(st)
+    ro = torch.zeros(4, 3)
+    with pytest.raises(RuntimeError, match='CUDA'):
+        m(ro, ro + 1, ro + 1, near=0.2, far=6, bg=1, stepsize=0.5, render_depth=True)
+
+
+def test_unsupported_grid_type_raises():
+    with pytest.raises(NotImplementedError):
+        k4nerf.DirectVoxGO([-1, -1, -1], [1, 1, 1], num_voxels=8 ** 3, num_voxels_base=8 ** 3, alpha_init=1e-2,
+                           density_type='TensoRFGrid')
