@@ -1,0 +1,436 @@
+#!/usr/bin/env python
+"""bench.py -- contract benchmark of the 4K-NeRF ray-march hot path on B200.
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Metric (BASELINE.json): rays/s of march + interp + MLP + composite.
+Workload: the north-star target -- BASELINE.json configs[1]'s model (DirectVoxGO fine stage,
+160^3 density + 12-ch feature grid, rgbnet 39->128->128->3, stepsize 0.5; configs/default.py:107-119)
+marched at 4K, 4032x3024 = 12.19 M rays per step, synthetic random-weight scene in the dense "FOG"
+regime (every in-box sample is interpolated, shaded and composited).  One
+"step" = one fused launch over one full frame; successive steps use different camera poses.  The
+same model at configs[1]'s nominal 1008x756 and the sparse "SHELL" regime are reported in `extra`.
+
+N > 1: one process per GPU, the frame's rows are sharded into N bands (k4nerf/dist.py), each
+rank marches its band and the packed bands are all-gathered with NCCL ("scaling": "strong").
+
+Timing: CUDA events on the launching stream around exactly K steps, barrier + synchronize on both
+sides, max over ranks.  Inputs per step (439 MB of rays + 213 MB of grids) exceed the 126 MB L2.
+
+`--impl reference`: the reference has NO CPU implementation of this path (every op is CUDA-only,
+lib/cuda/render_utils.cpp:46-48) and cannot be imported here, so the arm times the oracle port
+(oracle/pipeline.py: the reference's forward restated op-by-op on torch-CPU + C) on the host
+cores, each step a bounded 16384-ray sample of the same frame.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, '4k-nerf_b200'))
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+H4K, W4K = 3024, 4032
+HLR, WLR = 756, 1008
+GRID_RES = 160
+POSES = [(30.0, -30.0), (75.0, -20.0), (140.0, -35.0), (215.0, -25.0), (290.0, -30.0)]
+HBM_FALLBACK_GBS = 6650.0     # /opt/skills/guides/B200_PROFILING.md fallback
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--mlp-mode', default=None, help='fp32 | f16 | f16x3 (default: the package default)')
+    ap.add_argument('--regime', default='fog', choices=['fog', 'shell'])
+    ap.add_argument('--no-extra', action='store_true', help='skip the secondary measurements')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+# scene / rays (synthetic, seeded; built through the oracle's scene helpers = test infrastructure
+# used only to CREATE inputs; nothing of the oracle is on the timed path of the `ours` arm)
+# ------------------------------------------------------------------------------------------------
+def build_scene(regime):
+    sys.path.insert(0, os.path.join(ROOT, 'tests'))
+    from helpers import make_state, model_from_state
+    st = make_state('cfgA', res=GRID_RES, regime=regime)
+    return st, model_from_state
+
+
+def frame_rays_device(H, W, pose, dev):
+    """Pixel-centre rays of one view generated on the device (k4_make_rays)."""
+    import k4nerf
+    from oracle import scenes
+    K, c2w = scenes.blender_camera(H, W, theta=pose[0], phi=pose[1])
+    ro, rd, vd = k4nerf.get_rays_of_a_view(H, W, K, c2w.to(dev), ndc=False, inverse_y=False, flip_x=False, flip_y=False)
+    return ro.view(-1, 3), rd.view(-1, 3), vd.view(-1, 3)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
+         'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index=0):
+        self.rows = []
+        self.proc = None
+        self.gpu_index = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
+                                          '-lms', '100', '-i', str(self.gpu_index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self, t0, t1):
+        sm, mx, reasons = [], [], set()
+        for ts, line in self.rows:
+            if ts < t0 or ts > t1 + 0.2:
+                continue
+            f = [x.strip() for x in line.split(',')]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), f[5:9]):
+                if val.lower().startswith('active'):
+                    reasons.add(name)
+        if not sm:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0}
+        sm.sort()
+        return {'sm_mhz': sm[len(sm) // 2], 'sm_max_mhz': max(mx), 'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+def hbm_peak():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+        except Exception:
+            pass
+    return HBM_FALLBACK_GBS, 'fallback (B200_PROFILING.md 6.65 TB/s)'
+
+
+def algorithmic_bytes(n_rays, S_m, S_d, S_c, C=12):
+    """B = 68 N + S_m + 32 S_d + 32 C S_c (fp32 grids, no reuse credit)."""
+    return 68 * n_rays + S_m + 32 * S_d + 32 * C * S_c
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port on the host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_sample_rays(H, W, pose, n_chunks, chunk=8192):
+    """A bounded sample of the frame: `n_chunks` runs of `chunk` consecutive rays (the reference's
+    chunk size, run_sr.py:121-124) spread evenly over the image."""
+    from oracle import scenes
+    ro, rd, vd = scenes.blender_rays(H, W, theta=pose[0], phi=pose[1])
+    n = ro.shape[0]
+    outs = []
+    for c in range(n_chunks):
+        s = int((c + 0.5) * n / n_chunks) - chunk // 2
+        s = max(0, min(s, n - chunk))
+        outs.append((ro[s:s + chunk], rd[s:s + chunk], vd[s:s + chunk]))
+    return outs
+
+
+def cpu_time_step(st, chunks):
+    from oracle import ops, pipeline, scenes
+    t0 = time.perf_counter()
+    n = 0
+    for ro, rd, vd in chunks:
+        pipeline.forward(st, ro, rd, vd, ops.CpuOps, **scenes.RENDER_KW_DVGO)
+        n += ro.shape[0]
+    return n, time.perf_counter() - t0
+
+
+def run_reference_arm(args, rank):
+    """`--impl reference`: rank 0 alone runs; the other ranks exit 0 without work."""
+    if rank != 0:
+        return
+    from oracle import ops
+    cores = os.cpu_count() or 1
+    ops.set_num_threads(cores)
+    st, _ = build_scene(args.regime)
+    n_chunks = 2
+    for w in range(min(args.warmup, 1)):
+        cpu_time_step(st, cpu_sample_rays(H4K, W4K, POSES[w % len(POSES)], n_chunks))
+    tot_n, tot_t = 0, 0.0
+    for k in range(args.steps):
+        n, t = cpu_time_step(st, cpu_sample_rays(H4K, W4K, POSES[k % len(POSES)], n_chunks))
+        tot_n += n; tot_t += t
+    v = tot_n / tot_t
+    line = {
+        'impl': 'reference', 'metric': 'rays_per_s', 'value': v, 'unit': 'rays/s', 'n_gpus': args.gpus,
+        'steps': args.steps, 'warmup': min(args.warmup, 1), 'ms_per_step': 1e3 * tot_t / max(args.steps, 1),
+        'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': workload_config(args, 1),
+        'cpu_baseline': {'value': v, 'unit': 'rays/s', 'cores': cores, 'kind': 'port',
+                         'sample': f'{n_chunks} x 8192-ray chunks of the 4032x3024 frame per step (oracle/pipeline.py on torch-CPU + C, {cores} threads)'},
+        'e2e': {'value': v, 'unit': 'rays/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+        'note': 'the reference ships no CPU path for this op chain; this is the oracle port of it on the host cores',
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, n_gpus):
+    return {
+        'workload': 'north-star target: BASELINE configs[1] model (DirectVoxGO 160^3, k0 12 ch, rgbnet 39-128-128-3, '
+                    'stepsize 0.5) marched at 4032x3024 rays/step',
+        'regime': args.regime, 'rays_per_step': H4K * W4K, 'grid': [GRID_RES] * 3, 'k0_dim': 12,
+        'mlp': [39, 128, 128, 3], 'parallelism': f'row-bands x{n_gpus}' + (' + nccl all_gather' if n_gpus > 1 else ''),
+        'l2_policy': 'inputs larger than L2 (439 MB rays + 213 MB grids per step), pose changes every step',
+    }
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def main():
+    args = parse_args()
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+
+    if args.impl == 'reference':
+        run_reference_arm(args, rank)
+        return
+
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py: no CUDA device -- the k4nerf hot path has no CPU fallback')
+    import k4nerf
+    from k4nerf import dist as kdist
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=dev)
+    mode = args.mlp_mode or k4nerf.DirectVoxGO.mlp_mode
+
+    st, model_from_state = build_scene(args.regime)
+    model = model_from_state(st, dev)
+    kw = dict(near=2.0, far=6.0, bg=1, stepsize=0.5, inverse_y=False, flip_x=False, flip_y=False, render_depth=True)
+
+    # inputs resident in HBM before the timed region: one ray set per pose, this rank's band only
+    H, W = H4K, W4K
+    r0, r1 = kdist.band_range(H, rank, world)
+    bands = []
+    for pose in POSES:
+        ro, rd, vd = frame_rays_device(H, W, pose, dev)
+        sl = slice(r0 * W, r1 * W)
+        bands.append((ro[sl].clone(), rd[sl].clone(), vd[sl].clone()))
+        del ro, rd, vd
+    torch.cuda.empty_cache()
+    n_band = (r1 - r0) * W
+    n_pad = kdist.band_rows(H, world) * W
+    gathered = torch.empty(world * 5 * n_pad, device=dev, dtype=torch.float32) if world > 1 else None
+
+    def step(i):
+        ro, rd, vd = bands[i % len(bands)]
+        out = model.render_rays(ro, rd, vd, kw, image_hw=(r1 - r0, W), mlp_mode=mode)
+        if world > 1:
+            buf = kdist.pack_band(out, n_band, n_pad)
+            dist.all_gather_into_tensor(gathered, buf)
+        return out
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # algorithmic sample counts of pose 0 (device counters; equal to the oracle's counts, tests)
+    dbg = model.render_rays(*bands[0], kw, image_hw=(r1 - r0, W), mlp_mode=mode, debug=True)
+    counters = dbg['counters'].clone()
+    if world > 1:
+        dist.all_reduce(counters)
+    S_m, S_d, S_c, n_batches = [int(x) for x in counters.cpu().tolist()]
+    del dbg
+
+    for i in range(max(args.warmup, 3)):
+        step(i)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # per-launch kernel time of the dominant kernel, measured live on the launching stream
+    k_events = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    t_wall0 = time.time()
+    e0.record()
+    for i in range(args.steps):
+        ro, rd, vd = bands[i % len(bands)]
+        k_events[i][0].record()
+        out = model.render_rays(ro, rd, vd, kw, image_hw=(r1 - r0, W), mlp_mode=mode)
+        k_events[i][1].record()
+        if world > 1:
+            buf = kdist.pack_band(out, n_band, n_pad)
+            dist.all_gather_into_tensor(gathered, buf)
+    e1.record()
+    barrier()
+    t_wall1 = time.time()
+    ms_total = e0.elapsed_time(e1)
+    kernel_ms = sum(a.elapsed_time(b) for a, b in k_events) / max(args.steps, 1)
+    t = torch.tensor([ms_total, kernel_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total, kernel_ms = t.cpu().tolist()
+    if rank == 0:
+        time.sleep(0.2)
+        sampler.stop()
+    clocks = sampler.summary(t_wall0, t_wall1) if rank == 0 else None
+    ms_per_step = ms_total / max(args.steps, 1)
+    value = (H * W) / (ms_per_step * 1e-3)
+
+    # ---- e2e: the public API with HOST buffers (pinned rays in, host results out), every step ----
+    e2e = None
+    hb = [tuple(x.cpu().pin_memory() for x in bands[i]) for i in range(min(2, len(bands)))]
+    h_out = torch.empty(5 * n_band, dtype=torch.float32).pin_memory()
+
+    def e2e_step(i):
+        ro, rd, vd = [x.to(dev, non_blocking=True) for x in hb[i % len(hb)]]
+        out = model.render_rays(ro, rd, vd, kw, image_hw=(r1 - r0, W), mlp_mode=mode)
+        buf = kdist.pack_band(out, n_band, n_band)
+        if world > 1:
+            bufp = kdist.pack_band(out, n_band, n_pad)
+            dist.all_gather_into_tensor(gathered, bufp)
+        h_out.copy_(buf, non_blocking=True)
+
+    e2e_steps = max(2, min(args.steps, 3))
+    e2e_step(0)
+    barrier()
+    e0.record()
+    for i in range(e2e_steps):
+        e2e_step(i)
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = t.item() / e2e_steps
+    e2e = {'value': (H * W) / (e2e_ms * 1e-3), 'unit': 'rays/s',
+           'h2d_bytes_per_step': int(3 * 12 * H * W), 'd2h_bytes_per_step': int(20 * H * W),
+           'ms_per_step': e2e_ms, 'api': 'DirectVoxGO.render_rays on pinned host ray buffers, packed result copied back to pinned host memory'}
+    del hb
+
+    # ---- secondary measurements (rank 0 semantics, all ranks participate where collective) ----
+    extra = {}
+    if not args.no_extra and world == 1:
+        extra = secondary(model, st, model_from_state, kw, dev, mode, args)
+
+    if rank == 0:
+        peak, peak_src = hbm_peak()
+        alg_bytes = algorithmic_bytes(H * W, S_m, S_d, S_c)      # whole frame (all ranks)
+        achieved = alg_bytes / world / (kernel_ms * 1e-3) / 1e9   # per-launch bytes / per-launch time, GB/s
+        traffic = None
+        tp = os.path.join(ROOT, 'profiles', 'traffic.json')
+        if os.path.exists(tp):
+            try:
+                traffic = json.load(open(tp)).get('k4_march_kernel_bytes_per_launch')
+            except Exception:
+                traffic = None
+        line = {
+            'metric': 'rays_per_s', 'value': value, 'unit': 'rays/s', 'n_gpus': world, 'steps': args.steps,
+            'warmup': max(args.warmup, 3), 'ms_per_step': ms_per_step, 'higher_is_better': True,
+            'scaling': 'strong', 'vs_baseline': None, 'dtype': {'fp32': 'f32', 'f16': 'f16 (fp32 accumulate)',
+                                                                'f16x3': 'f16x3 split (fp32-equivalent)'}[mode],
+            'data': 'synthetic', 'config': workload_config(args, world), 'mlp_mode': mode,
+            'e2e': e2e, 'gpu_launches': args.steps, 'clocks': clocks,
+            'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
+                         'traffic': traffic, 'peak_source': peak_src, 'kernel': 'k4_march_kernel',
+                         'kernel_ms_per_launch': kernel_ms,
+                         'algorithmic_bytes_per_ray': alg_bytes / (H * W),
+                         'samples_per_ray': {'S_m': S_m / (H * W), 'S_d': S_d / (H * W), 'S_c': S_c / (H * W)},
+                         'note': 'logical bytes (no reuse credit): the 213 MB scene is L2/L1 resident, so DRAM traffic is far below this'},
+        }
+        if extra:
+            line['extra'] = extra
+        if not args.no_cpu_baseline and world == 1:
+            line['cpu_baseline'] = cpu_baseline(st)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def time_mode(model, rays, kw, hw, mode, iters=3):
+    for _ in range(2):
+        model.render_rays(*rays, kw, image_hw=hw, mlp_mode=mode)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        model.render_rays(*rays, kw, image_hw=hw, mlp_mode=mode)
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def secondary(model, st, model_from_state, kw, dev, mode, args):
+    """configs[1] at its nominal 1008x756, and the sparse SHELL regime, same kernel and mode."""
+    from helpers import make_state
+    out = {}
+    rays = frame_rays_device(HLR, WLR, POSES[0], dev)
+    ms = time_mode(model, rays, kw, (HLR, WLR), mode)
+    out['configs[1]_1008x756_' + args.regime] = {'rays_per_s': HLR * WLR / (ms * 1e-3), 'ms_per_frame': ms}
+    other = 'shell' if args.regime == 'fog' else 'fog'
+    st2 = make_state('cfgA', res=GRID_RES, regime=other)
+    m2 = model_from_state(st2, dev)
+    rays4k = frame_rays_device(H4K, W4K, POSES[0], dev)
+    dbg = m2.render_rays(*rays4k, kw, image_hw=(H4K, W4K), mlp_mode=mode, debug=True)
+    c = [int(x) for x in dbg['counters'].cpu().tolist()]
+    ms = time_mode(m2, rays4k, kw, (H4K, W4K), mode)
+    n = H4K * W4K
+    peak, _ = hbm_peak()
+    b = algorithmic_bytes(n, c[0], c[1], c[2])
+    out['4032x3024_' + other] = {'rays_per_s': n / (ms * 1e-3), 'ms_per_frame': ms,
+                                 'algorithmic_bytes_per_ray': b / n, 'roofline_frac': b / (ms * 1e-3) / 1e9 / peak,
+                                 'samples_per_ray': {'S_m': c[0] / n, 'S_d': c[1] / n, 'S_c': c[2] / n}}
+    return out
+
+
+def cpu_baseline(st):
+    """The oracle port timed on the host cores, bounded sample (rank 0, N=1 only)."""
+    from oracle import ops
+    cores = os.cpu_count() or 1
+    ops.set_num_threads(cores)
+    chunks = cpu_sample_rays(H4K, W4K, POSES[0], 2)
+    cpu_time_step(st, chunks[:1])                 # warm-up
+    n, t = cpu_time_step(st, chunks)
+    return {'value': n / t, 'unit': 'rays/s', 'cores': cores, 'kind': 'port',
+            'sample': f'2 x 8192-ray chunks of the 4032x3024 frame ({t:.1f} s; oracle/pipeline.py, torch-CPU + C, {cores} threads)'}
+
+
+if __name__ == '__main__':
+    main()
