@@ -172,6 +172,41 @@ def _segment_sum(src, index, out):
     return out.index_add_(0, index, src)
 
 
+def _early_out_counts(ids_m, ids_d, ids_a, i_end, alphainv_last, N):
+    """Per-ray sample counts with the transmittance early-out applied.
+
+    The reference materialises every in-box sample before it knows where a ray saturates
+    (render_utils_kernel.cu:597 only zeroes the later weights), so its mask lookups / density fetches
+    cover ALL in-box samples (`S_m_all`, `S_d_all`).  A marcher that stops at the early-out never
+    visits the samples behind it; SURVEY.md section 8(d) defines the roofline counts on those visited
+    samples.  Returns int64 [N,2]: in-box samples and occupancy hits with step <= the step of the
+    last composited sample of the ray (all of them for rays that never reached T < 1e-3)."""
+    ray_a, step_a = ids_a
+    dev = alphainv_last.device
+    big = torch.iinfo(torch.int64).max
+    last_step = torch.full((N,), big, dtype=torch.int64, device=dev)
+    if ray_a.numel():
+        term = (alphainv_last.double() < 1e-3) & (i_end > 0)
+        idx = (i_end - 1).clamp(min=0)
+        last_step = torch.where(term, step_a[idx.clamp(max=ray_a.numel() - 1)], last_step)
+    out = torch.zeros((N, 2), dtype=torch.int64, device=dev)
+    for col, (rid, sid) in enumerate((ids_m, ids_d)):
+        keep = sid <= last_step[rid]
+        out[:, col] = torch.zeros(N, dtype=torch.int64, device=dev).index_add_(0, rid[keep], torch.ones_like(rid[keep]))
+    return out
+
+
+def _add_stats(stats, ids_m, ids_d, S_c, ray_stats, ray_id_c, N):
+    """S_m/S_d: visited before the early-out (what a fused marcher touches); *_all: what the
+    reference's unfused pipeline touches; S_c: samples shaded (identical in both)."""
+    stats['S_m'] = stats.get('S_m', 0) + int(ray_stats[:, 0].sum())
+    stats['S_d'] = stats.get('S_d', 0) + int(ray_stats[:, 1].sum())
+    stats['S_c'] = stats.get('S_c', 0) + S_c
+    stats['S_m_all'] = stats.get('S_m_all', 0) + ids_m[0].shape[0]
+    stats['S_d_all'] = stats.get('S_d_all', 0) + ids_d[0].shape[0]
+    stats['n_rays'] = stats.get('n_rays', 0) + N
+
+
 # ----------------------------------------------------------------------------------------------
 # forward passes
 # ----------------------------------------------------------------------------------------------
@@ -192,13 +227,13 @@ def dvgo_forward(st, rays_o, rays_d, viewdirs, ops, stats=None, **render_kwargs)
     ray_id = ray_id[mask_inbbox]
     step_id = step_id[mask_inbbox]
     interval = float(render_kwargs['stepsize'] * st['voxel_size_ratio'])
-    S_m = ray_pts.shape[0]
+    ids_m = (ray_id, step_id)
 
     mask1 = mask_grid(st['mask_cache'], ray_pts, ops)
     ray_pts = ray_pts[mask1]
     ray_id = ray_id[mask1]
     step_id = step_id[mask1]
-    S_d = ray_pts.shape[0]
+    ids_d = (ray_id, step_id)
 
     density = dense_grid(st['density'], ray_pts, st['xyz_min'], st['xyz_max'])
     alpha = ops.raw2alpha(density.flatten().contiguous(), float(st['act_shift']), interval)[1].reshape(density.shape)
@@ -209,7 +244,8 @@ def dvgo_forward(st, rays_o, rays_d, viewdirs, ops, stats=None, **render_kwargs)
         step_id = step_id[mask2]
         alpha = alpha[mask2]
 
-    weights, _, alphainv_last = ops.alpha2weight(alpha.contiguous(), ray_id.contiguous(), N)[:3]
+    weights, _, alphainv_last, _, i_end = ops.alpha2weight(alpha.contiguous(), ray_id.contiguous(), N)
+    ray_stats = _early_out_counts(ids_m, ids_d, (ray_id, step_id), i_end, alphainv_last, N) if stats is not None else None
     if st['fast_color_thres'] > 0:
         mask3 = (weights > st['fast_color_thres'])
         weights = weights[mask3]
@@ -249,10 +285,8 @@ def dvgo_forward(st, rays_o, rays_d, viewdirs, ops, stats=None, **render_kwargs)
     if render_kwargs.get('render_depth', False):
         ret['depth'] = _segment_sum(weights * s, ray_id, torch.zeros([N], device=dev))
     if stats is not None:
-        stats['S_m'] = stats.get('S_m', 0) + S_m
-        stats['S_d'] = stats.get('S_d', 0) + S_d
-        stats['S_c'] = stats.get('S_c', 0) + S_c
-        stats['n_rays'] = stats.get('n_rays', 0) + N
+        _add_stats(stats, ids_m, ids_d, S_c, ray_stats, ray_id, N)
+        ret['_ray_stats'] = ray_stats
         ret['_N_steps'] = N_steps
         ret['_t_min'] = t_min
         ret['_t_max'] = t_max
@@ -276,13 +310,13 @@ def dmpigo_forward(st, rays_o, rays_d, viewdirs, ops, stats=None, **render_kwarg
     ray_id = torch.arange(mask_inbbox.shape[0], device=dev).view(-1, 1).expand_as(mask_inbbox)[mask_inbbox]
     step_id = torch.arange(mask_inbbox.shape[1], device=dev).view(1, -1).expand_as(mask_inbbox)[mask_inbbox]
     interval = float(render_kwargs['stepsize'] * st['voxel_size_ratio'])
-    S_m = ray_pts.shape[0]
+    ids_m = (ray_id, step_id)
 
     mask1 = mask_grid(st['mask_cache'], ray_pts, ops)
     ray_pts = ray_pts[mask1]
     ray_id = ray_id[mask1]
     step_id = step_id[mask1]
-    S_d = ray_pts.shape[0]
+    ids_d = (ray_id, step_id)
 
     density = dense_grid(st['density'], ray_pts, st['xyz_min'], st['xyz_max']) + \
         dense_grid(st['act_shift_grid'], ray_pts, st['xyz_min'], st['xyz_max'])
@@ -294,7 +328,8 @@ def dmpigo_forward(st, rays_o, rays_d, viewdirs, ops, stats=None, **render_kwarg
         step_id = step_id[mask2]
         alpha = alpha[mask2]
 
-    weights, _, alphainv_last = ops.alpha2weight(alpha.contiguous(), ray_id.contiguous(), N)[:3]
+    weights, _, alphainv_last, _, i_end = ops.alpha2weight(alpha.contiguous(), ray_id.contiguous(), N)
+    ray_stats = _early_out_counts(ids_m, ids_d, (ray_id, step_id), i_end, alphainv_last, N) if stats is not None else None
     if st['fast_color_thres'] > 0:
         mask3 = (weights > st['fast_color_thres'])
         ray_pts = ray_pts[mask3]
@@ -330,10 +365,8 @@ def dmpigo_forward(st, rays_o, rays_d, viewdirs, ops, stats=None, **render_kwarg
     if render_kwargs.get('render_depth', False):
         ret['depth'] = _segment_sum(weights * s, ray_id, torch.zeros([N], device=dev))
     if stats is not None:
-        stats['S_m'] = stats.get('S_m', 0) + S_m
-        stats['S_d'] = stats.get('S_d', 0) + S_d
-        stats['S_c'] = stats.get('S_c', 0) + S_c
-        stats['n_rays'] = stats.get('n_rays', 0) + N
+        _add_stats(stats, ids_m, ids_d, S_c, ray_stats, ray_id, N)
+        ret['_ray_stats'] = ray_stats
         ret['_step_id'] = step_id
     return ret
 
