@@ -49,8 +49,8 @@ __device__ __forceinline__ Ray setup_ray_dvgo(const K4Dev& s, const K4RenderPara
     const float bz = __fdiv_rn(__fsub_rn(s.xyz_min[2], o.z), vz);
     r.t_min = fmaxf(fminf(fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fminf(az, bz)), rp.far_), rp.near_);
     r.t_max = fmaxf(fminf(fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz)), rp.far_), rp.near_);
-    float nn = __fmul_rn(d.x, d.x);
-    nn = __fmaf_rn(d.y, d.y, nn);
+    float nn = __fmul_rn(d.y, d.y);              // reference SASS: FMUL y,y ; FFMA x,x,. ; FFMA z,z,.
+    nn = __fmaf_rn(d.x, d.x, nn);
     nn = __fmaf_rn(d.z, d.z, nn);
     const float rnorm = __fsqrt_rn(nn);
     const float ns = ceilf(__fdiv_rn(__fmul_rn(__fsub_rn(r.t_max, r.t_min), rnorm), rp.stepdist));

@@ -71,10 +71,11 @@ K4O_API void k4o_infer_t_minmax(const float* rays_o, const float* rays_d,
     }
 }
 
-/* squared norm as nvcc contracts `x*x + y*y + z*z`: fma(z,z, fma(y,y, x*x)). */
+/* squared norm as nvcc contracts `x*x + y*y + z*z` in the reference build (SASS of
+ * infer_n_samples / infer_ray_start_dir: FMUL y,y ; FFMA x,x,. ; FFMA z,z,.): fma(z,z, fma(x,x, y*y)). */
 static inline float k4o_rnorm(const float* d) {
-    float s = d[0] * d[0];
-    s = fmaf(d[1], d[1], s);
+    float s = d[1] * d[1];
+    s = fmaf(d[0], d[0], s);
     s = fmaf(d[2], d[2], s);
     return sqrtf(s);
 }
