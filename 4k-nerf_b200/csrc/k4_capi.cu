@@ -80,6 +80,35 @@ __global__ void pack_w_f16_kernel(const float* __restrict__ W, __half* __restric
     lo[i] = __float2half_rn(w - __half2float(h));
 }
 
+// tcgen05 operand tiles (canonical K-major, no swizzle; see tc_canon_off)
+__global__ void pack_tc_weight_kernel(const float* __restrict__ W, unsigned char* __restrict__ dst,
+                                      int n_out, int n_in, int npad, int kpad) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npad * kpad) return;
+    const int n = i / kpad, k = i - n * kpad;
+    const float w = (n < n_out && k < n_in) ? W[(size_t)n * n_in + k] : 0.f;
+    *reinterpret_cast<__half*>(dst + tc_canon_off(n, k >> 3, kpad >> 3) + (k & 7) * 2) = __float2half_rn(w);
+}
+// bias tile [npad][16]: col 0 = fp16(b), col 1 = fp16(b - col0); multiplied by the ONES tile (cols 0,1 = 1)
+__global__ void pack_tc_bias_kernel(const float* __restrict__ b, unsigned char* __restrict__ dst, int n_out, int npad) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npad * 16) return;
+    const int n = i / 16, k = i - n * 16;
+    float v = 0.f;
+    if (n < n_out && k < 2) {
+        const float bb = b[n];
+        const __half hi = __float2half_rn(bb);
+        v = (k == 0) ? __half2float(hi) : (bb - __half2float(hi));
+    }
+    *reinterpret_cast<__half*>(dst + tc_canon_off(n, k >> 3, 2) + (k & 7) * 2) = __float2half_rn(v);
+}
+__global__ void pack_tc_ones_kernel(unsigned char* __restrict__ dst) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 128 * 16) return;
+    const int n = i / 16, k = i - n * 16;
+    *reinterpret_cast<__half*>(dst + tc_canon_off(n, k >> 3, 2) + (k & 7) * 2) = __float2half_rn(k < 2 ? 1.f : 0.f);
+}
+
 // get_rays / ndc_rays / get_rays_of_a_view (lib/dvgo.py:516-582), mode='center'
 struct RayGenParams {
     float K[9];
@@ -269,6 +298,23 @@ extern "C" int k4_scene_create(const k4_scene_desc* d, k4_stream_t stream, k4_sc
                     v.wh[l] = ph; v.wl[l] = pl;
                 }
             }
+            // tcgen05 blob (k4_march_tc.cu): only for the shapes that kernel is instantiated for
+            if ((v.width == 128 || v.width == 64) && dim0 <= 64) {
+                const int kpad = round_up(dim0, 16), w = v.width;
+                const TcBlobLayout BL = tc_blob_layout(kpad, w);
+                unsigned char* blob = nullptr;
+                K4_TRY(scene_alloc(sc, (void**)&blob, (size_t)BL.total));
+                K4_CTRY(cudaMemsetAsync(blob, 0, BL.total, s));
+                pack_tc_weight_kernel<<<(w * kpad + 255) / 256, 256, 0, s>>>(d->d_rgbnet_weight[0], blob + BL.off_w1, w, dim0, w, kpad);
+                pack_tc_weight_kernel<<<(w * w + 255) / 256, 256, 0, s>>>(d->d_rgbnet_weight[1], blob + BL.off_w2, w, w, w, w);
+                pack_tc_weight_kernel<<<(16 * w + 255) / 256, 256, 0, s>>>(d->d_rgbnet_weight[2], blob + BL.off_w3, 3, w, 16, w);
+                pack_tc_bias_kernel<<<(w * 16 + 255) / 256, 256, 0, s>>>(d->d_rgbnet_bias[0], blob + BL.off_b1, w, w);
+                pack_tc_bias_kernel<<<(w * 16 + 255) / 256, 256, 0, s>>>(d->d_rgbnet_bias[1], blob + BL.off_b2, w, w);
+                pack_tc_bias_kernel<<<1, 256, 0, s>>>(d->d_rgbnet_bias[2], blob + BL.off_b3, 3, 16);
+                pack_tc_ones_kernel<<<8, 256, 0, s>>>(blob + BL.off_ones);
+                K4_CTRY(cudaGetLastError());
+                v.tc_blob = blob; v.tc_kpad = kpad; v.tc_width = w;
+            }
         }
     }
 #undef K4_TRY
@@ -327,6 +373,10 @@ extern "C" int k4_render_rays(const k4_scene* sc, const k4_render_args* a,
     rp.ray_stats = out->d_ray_stats; rp.t_minmax = out->d_t_minmax; rp.counters = out->d_counters;
     rp.tile_counter = reinterpret_cast<unsigned int*>(d_workspace);
     K4_CUDA_TRY(cudaMemsetAsync(d_workspace, 0, 16, s));
+    if (a->mlp_mode == K4_MLP_TCGEN05 && v.depth > 0) {
+        if (!k4_tc_supported(v)) return K4_ERR_UNSUPPORTED;
+        return k4_launch_march_tc(sc, rp, s);
+    }
     return k4_launch_march(sc, rp, a->mlp_mode, s);
 }
 

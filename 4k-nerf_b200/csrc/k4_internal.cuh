@@ -32,7 +32,36 @@ struct K4Dev {
     const __half* wh[K4_MAX_MLP_LAYERS];
     const __half* wl[K4_MAX_MLP_LAYERS];
     int kpad[K4_MAX_MLP_LAYERS], npad[K4_MAX_MLP_LAYERS];
+    // tcgen05 pack: one blob of canonical K-major (no swizzle) UMMA operand tiles, see tc_blob_layout()
+    const unsigned char* tc_blob;
+    int tc_kpad, tc_width;
 };
+
+// ---- tcgen05 operand blob (built by k4_scene_create, staged by one TMA bulk copy) -----------------
+// Canonical K-major SWIZZLE_NONE layout of a [rows][K] fp16 tile with K/8 16-byte chunks per row:
+// byte offset of (row r, chunk kc) = (r/8)*(kchunks*128) + kc*128 + (r%8)*16, i.e. 8x16B "core
+// matrices", LBO = 128 B between K chunks, SBO = kchunks*128 B between 8-row groups.
+__host__ __device__ inline int tc_canon_off(int r, int kc, int kchunks) {
+    return (r >> 3) * (kchunks * 128) + kc * 128 + (r & 7) * 16;
+}
+struct TcBlobLayout {
+    int off_w1, off_w2, off_w3, off_b1, off_b2, off_b3, off_ones, total;
+};
+// W1 [W][kpad], W2 [W][W], W3 [16][W], bias tiles B1/B2 [W][16], B3 [16][16] (col 0 = fp16(b),
+// col 1 = fp16(b - col0)), ONES [128][16] (cols 0,1 = 1): every layer's bias is one extra K=16 MMA.
+__host__ __device__ inline TcBlobLayout tc_blob_layout(int kpad, int w) {
+    TcBlobLayout L;
+    int o = 0;
+    L.off_w1 = o; o += w * kpad * 2;
+    L.off_w2 = o; o += w * w * 2;
+    L.off_w3 = o; o += 16 * w * 2;
+    L.off_b1 = o; o += w * 16 * 2;
+    L.off_b2 = o; o += w * 16 * 2;
+    L.off_b3 = o; o += 16 * 16 * 2;
+    L.off_ones = o; o += 128 * 16 * 2;
+    L.total = o;
+    return L;
+}
 
 struct k4_scene {
     K4Dev dev;
@@ -71,3 +100,5 @@ void k4_set_cuda_error(cudaError_t e, const char* where);
 
 // launchers
 int k4_launch_march(const k4_scene* sc, const K4RenderParams& rp, int mlp_mode, cudaStream_t st);
+int k4_launch_march_tc(const k4_scene* sc, K4RenderParams rp, cudaStream_t st);   // K4_ERR_UNSUPPORTED if the shape has no tcgen05 build
+bool k4_tc_supported(const K4Dev& v);

@@ -16,7 +16,7 @@ from helpers import compare, make_state, model_from_state, rays_for
 
 pytestmark = pytest.mark.gpu
 
-PSNR_BAR = {'fp32': 80.0, 'f16x3': 70.0, 'f16': 55.0}
+PSNR_BAR = {'fp32': 80.0, 'f16x3': 70.0, 'f16': 55.0, 'tc': 55.0}
 
 
 def run_both(st, rays, kw, dev, mode, image_hw=None):
@@ -51,7 +51,7 @@ def check_geometry(ours, ref, stats, st, n):
 
 
 @pytest.mark.parametrize('regime', ['fog', 'shell'])
-@pytest.mark.parametrize('mode', ['fp32', 'f16x3', 'f16'])
+@pytest.mark.parametrize('mode', ['fp32', 'f16x3', 'f16', 'tc'])
 def test_cfgA_parity(cuda_device, regime, mode):
     st = make_state('cfgA', res=48, regime=regime)
     rays, kw = rays_for(st, 40, 52)
@@ -64,7 +64,7 @@ def test_cfgA_parity(cuda_device, regime, mode):
     assert cmp['depth_maxabs'] <= 2e-5, cmp
 
 
-@pytest.mark.parametrize('mode', ['fp32', 'f16x3'])
+@pytest.mark.parametrize('mode', ['fp32', 'f16x3', 'tc'])
 def test_cfgA_2d_tiles_equal_linear_order(cuda_device, mode):
     """8x4 pixel-tile scheduling must not change any ray's result."""
     st = make_state('cfgA', res=32, regime='shell')
@@ -79,7 +79,7 @@ def test_cfgA_2d_tiles_equal_linear_order(cuda_device, mode):
     if mode == 'fp32':
         assert torch.equal(a['rgb_marched'], b['rgb_marched'])
     else:
-        assert (a['rgb_marched'] - b['rgb_marched']).abs().max().item() < 1e-5
+        assert (a['rgb_marched'] - b['rgb_marched']).abs().max().item() < (1e-5 if mode != 'tc' else 2e-5)
 
 
 def test_cfgA_not_direct_and_width64(cuda_device):
@@ -104,7 +104,7 @@ def test_cfg1_colour_grid_no_mlp(cuda_device):
 
 
 @pytest.mark.parametrize('regime', ['fog', 'shell'])
-@pytest.mark.parametrize('mode', ['fp32', 'f16x3', 'f16'])
+@pytest.mark.parametrize('mode', ['fp32', 'f16x3', 'f16', 'tc'])
 def test_cfgB_mpi_parity(cuda_device, regime, mode):
     st = make_state('cfgB', xy=48, depth=32, regime=regime)
     rays, kw = rays_for(st, 30, 40)
@@ -141,11 +141,11 @@ def test_edge_cases(cuda_device):
     ro, rd, vd = ro.repeat(9, 1)[:33], rd.repeat(9, 1)[:33], vd.repeat(9, 1)[:33]
     stats = {}
     ref = pipeline.forward(st, ro, rd, vd, ops.CpuOps, stats=stats, **kw)
-    for mode in ('fp32', 'f16x3'):
+    for mode in ('fp32', 'f16x3', 'tc'):
         ours = m.render_rays(ro.to(dev), rd.to(dev), vd.to(dev), kw, mlp_mode=mode, debug=True)
         check_geometry(ours, ref, stats, st, 33)
         cmp = compare(ours, ref, 33)
-        assert cmp['rgb_marched_maxabs'] < 1e-4, (mode, cmp)
+        assert cmp['rgb_marched_maxabs'] < (1e-4 if mode != 'tc' else 5e-3), (mode, cmp)
         assert torch.equal(ours['alphainv_last'][1].cpu(), torch.tensor(1.0))   # missed the box: T stays 1
 
 
