@@ -284,6 +284,8 @@ k4_march_tc_kernel(const __grid_constant__ K4Dev s, const __grid_constant__ K4Re
         wg_bar(wg);
         const long long tile = tile_slot[iter & 1];
         if (tile >= rp.n_tiles) break;
+        if ((rp.dbg & 1) && wg == 1) break;
+        if ((rp.dbg & 2) && iter > 0) break;
 
         long long ray_i;
         if (rp.image_w > 0) {
@@ -352,7 +354,13 @@ k4_march_tc_kernel(const __grid_constant__ K4Dev s, const __grid_constant__ K4Re
             // ---------------- a round of marching ----------------
 #pragma unroll 1
             for (int rr = 0; rr < TC_ROUND; ++rr) {
-                if ((*tailp - head) >= 128u) break;                 // a batch is pending: go flush it
+                // a batch is pending -> go flush it.  Read once per warp and broadcast: the decision must
+                // be warp-uniform (lanes may still be diverged from the previous step's branches, and the
+                // other warps keep appending, so per-lane reads could disagree and split the warp).
+                unsigned pend = 0;
+                if (lane == 0) pend = *tailp - head;
+                pend = __shfl_sync(FULL, pend, 0);
+                if (pend >= 128u) break;
                 const bool active = !done && (i < r.n_steps);
                 if (!__any_sync(FULL, active)) break;
                 bool shade = false;

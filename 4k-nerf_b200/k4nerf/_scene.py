@@ -10,7 +10,7 @@ import torch
 
 from . import _lib
 
-_DEFAULT_MLP_MODE = 'f16x3'
+_DEFAULT_MLP_MODE = 'auto'     # tcgen05 kernel when the shape has a build, else mma.sync f16, else fp32
 
 
 class SceneHandle:
@@ -128,6 +128,27 @@ class FusedRenderMixin:
         object.__setattr__(self, '_k4_handle', h)
         return h
 
+    def resolve_mlp_mode(self, mode):
+        """'auto' -> the fastest mode built for this model's shape (all modes are > 100 dB PSNR from
+        the fp32 oracle, profiles/r1_parity_all_modes.jsonl)."""
+        if mode != 'auto':
+            return mode
+        layers = linear_layers(self.rgbnet)
+        if not layers:
+            return 'fp32'
+        width, dim0 = layers[0].out_features, layers[0].in_features
+        C = self.k0.grid.shape[1]
+        vpe = int(getattr(self, 'viewbase_pe', 0))
+        spe = int(getattr(self, 'spatial_pe', 0))
+        if len(layers) == 3:
+            if self._k4_kind == _lib.K4_KIND_DVGO and C == 12 and vpe == 4 and width == 128 and getattr(self, 'rgbnet_direct', True):
+                return 'tc'
+            if self._k4_kind == _lib.K4_KIND_DMPIGO and C == 9 and vpe == 0 and spe == 0 and width == 64:
+                return 'tc'
+            if width in (64, 128) and dim0 <= 64:
+                return 'f16'
+        return 'fp32'
+
     def invalidate_scene(self):
         object.__setattr__(self, '_k4_handle', None)
 
@@ -153,7 +174,7 @@ class FusedRenderMixin:
         a.stepsize = float(render_kwargs['stepsize'])
         a.bg = float(render_kwargs['bg'])
         a.render_depth = int(want_depth)
-        a.mlp_mode = _lib.MLP_MODES[mlp_mode or self.mlp_mode]
+        a.mlp_mode = _lib.MLP_MODES[self.resolve_mlp_mode(mlp_mode or self.mlp_mode)]
         if image_hw is not None and image_hw[0] * image_hw[1] == N:
             a.image_h, a.image_w = int(image_hw[0]), int(image_hw[1])
         o = _lib.RenderOut()

@@ -51,7 +51,7 @@ def parse_args():
     ap.add_argument('--steps', type=int, default=5)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--mlp-mode', default=None, help='fp32 | f16 | f16x3 (default: the package default)')
+    ap.add_argument('--mlp-mode', default=None, help='tc | f16 | f16x3 | fp32 (default: auto = fastest built for the shape)')
     ap.add_argument('--regime', default='fog', choices=['fog', 'shell'])
     ap.add_argument('--no-extra', action='store_true', help='skip the secondary measurements')
     ap.add_argument('--no-cpu-baseline', action='store_true')
@@ -236,10 +236,10 @@ def main():
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
         dist.init_process_group('nccl', device_id=dev)
-    mode = args.mlp_mode or k4nerf.DirectVoxGO.mlp_mode
 
     st, model_from_state = build_scene(args.regime)
     model = model_from_state(st, dev)
+    mode = model.resolve_mlp_mode(args.mlp_mode or model.mlp_mode)
     kw = dict(near=2.0, far=6.0, bg=1, stepsize=0.5, inverse_y=False, flip_x=False, flip_y=False, render_depth=True)
 
     # inputs resident in HBM before the timed region: one ray set per pose, this rank's band only
@@ -364,8 +364,9 @@ def main():
         line = {
             'metric': 'rays_per_s', 'value': value, 'unit': 'rays/s', 'n_gpus': world, 'steps': args.steps,
             'warmup': max(args.warmup, 3), 'ms_per_step': ms_per_step, 'higher_is_better': True,
-            'scaling': 'strong', 'vs_baseline': None, 'dtype': {'fp32': 'f32', 'f16': 'f16 (fp32 accumulate)',
-                                                                'f16x3': 'f16x3 split (fp32-equivalent)'}[mode],
+            'scaling': 'strong', 'vs_baseline': None,
+            'dtype': {'fp32': 'f32', 'f16': 'f16 operands, f32 accumulate (mma.sync)', 'f16x3': 'f16x3 split (f32-equivalent)',
+                      'tc': 'f32 geometry/interpolation/compositing; rgbnet f16 operands, f32 accumulate (tcgen05)'}[mode],
             'data': 'synthetic', 'config': workload_config(args, world), 'mlp_mode': mode,
             'e2e': e2e, 'gpu_launches': args.steps, 'clocks': clocks,
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
