@@ -370,7 +370,8 @@ def main():
             'data': 'synthetic', 'config': workload_config(args, world), 'mlp_mode': mode,
             'e2e': e2e, 'gpu_launches': args.steps, 'clocks': clocks,
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-                         'traffic': traffic, 'peak_source': peak_src, 'kernel': 'k4_march_kernel',
+                         'traffic': traffic, 'peak_source': peak_src,
+                         'kernel': 'k4_march_tc_kernel' if mode == 'tc' else 'k4_march_kernel',
                          'kernel_ms_per_launch': kernel_ms,
                          'algorithmic_bytes_per_ray': alg_bytes / (H * W),
                          'samples_per_ray': {'S_m': S_m / (H * W), 'S_d': S_d / (H * W), 'S_c': S_c / (H * W)},
