@@ -1,0 +1,638 @@
+// k4_sr.cu -- the VC-Decoder (SFTNet, lib/sr_esrnet.py:400-465) on sm_100a.
+//
+// Replaces the reference's 229 cuDNN convolutions + torch.cat copies + F.interpolate + leaky_relu
+// launches per tile with
+//
+//   conv3x3_tc_kernel<N>   every 3x3 convolution as an im2col-free implicit GEMM on tcgen05:
+//       a CTA owns a 16x8 pixel tile (M = 128 rows = y*8+x); per 32-channel slice of the input the
+//       (16+2)x(8+2) halo is staged ONCE in shared memory as four 8-channel planes
+//       [plane][hy][hx] x 16 B -- which IS the canonical K-major UMMA layout (core matrix = 8
+//       horizontally adjacent pixels, SBO = halo row pitch, LBO = plane pitch) -- so the nine taps
+//       are nine shared-memory descriptors that differ only in their start address
+//       (+dy*ROW + dx*16 B); weights are pre-packed per (slice, tap) as [N][32] K-major tiles;
+//       fp32 accumulators live in TMEM for the whole K loop (9 taps x Cin/16 MMAs), loads of slice
+//       c+1 (cp.async, zero-fill = the conv's zero padding) overlap the MMAs of slice c;
+//       dense-block concatenation is free (a conv reads channels [0,Cin) of the block's NHWC buffer
+//       and writes its growth channels behind them), nearest-x2 upsampling is folded into the halo
+//       addressing, bias / LeakyReLU / residual scaling / trunk update are the epilogue;
+//   sft_kernel             SFTLayer (lib/sr_esrnet.py:112-123): both 1x1-conv branches + modulation,
+//       one thread per pixel, weights in shared memory, fp32;
+//   condnet_kernel         CondNet (lib/sr_esrnet.py:440-444), one thread per pixel, fp32.
+//
+// Numerics: conv operands are fp16 (weights and activations), accumulation fp32 in TMEM, the
+// residual trunk and all SFT / CondNet math stay fp32.  (The reference itself runs these convs with
+// TF32 operands: torch.backends.cudnn.allow_tf32 defaults to True.)
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "k4_internal.cuh"
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------
+// tcgen05 plumbing (same encodings as k4_march_tc.cu; cute/arch/mma_sm100_desc.hpp)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t sr_s32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint64_t sr_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46);
+}
+__device__ __forceinline__ uint32_t sr_idesc(int m, int n) { return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24); }
+__device__ __forceinline__ void sr_mma_ss(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n}\n"
+                 :: "r"(d), "l"(a), "l"(b), "r"(idesc), "r"(acc), "r"(0u) : "memory");
+}
+__device__ __forceinline__ void sr_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" :: "r"(sr_s32(bar)) : "memory");
+}
+__device__ __forceinline__ void sr_mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" :: "r"(sr_s32(bar)), "r"(count));
+}
+__device__ __forceinline__ void sr_mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok = 0;
+    while (!ok) {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                     : "=r"(ok) : "r"(sr_s32(bar)), "r"(parity) : "memory");
+    }
+}
+__device__ __forceinline__ void sr_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                 : "r"(taddr));
+}
+__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src, int src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" :: "r"(sr_s32(dst_smem)), "l"(src), "r"(src_bytes) : "memory");
+}
+
+constexpr int SR_TY = 16, SR_TX = 8;                 // output tile (pixels)
+constexpr int SR_HY = SR_TY + 2, SR_HX = SR_TX + 2;  // halo
+constexpr int SR_ROW = SR_HX * 16;                   // 160 B: one halo row of one 8-channel plane
+constexpr int SR_PLANE = SR_HY * SR_ROW;             // 2880 B
+constexpr int SR_CK = 32;                            // input channels per K slice
+constexpr int SR_A_STAGE = (SR_CK / 8) * SR_PLANE;   // 11520 B
+
+enum { SRM_STORE_F16 = 0,      // dst_h[c0..c0+N) = act(acc + b)
+       SRM_TRUNK = 1,          // dst_f = (acc + b) * scale + add_f                  (conv5: x5*0.2 + x)
+       SRM_ADD_STORE_F16 = 2,  // dst_h = fp16((acc + b) + add_f)                    (conv_body + feat)
+       SRM_STORE_F32F16 = 3,   // dst_f = acc + b (fp32, 64 ch) and dst_h = fp16     (conv_first: trunk + feat)
+       SRM_OUT_NCHW = 4 };     // out_nchw[c][y][x] = acc + b, c < n_valid          (conv_last)
+
+struct ConvParams {
+    const __half* src; int src_cstride; int src_c0; int cin;       // cin: multiple of 32 (zero padded weights beyond the real Cin)
+    int H, W; int upsample;                                        // output size; upsample: src is (H/2) x (W/2), nearest
+    const unsigned char* wpack; const float* bias;
+    int mode; float lrelu; float scale;
+    __half* dst_h; int dst_cstride; int dst_c0;
+    float* dst_f; const float* add_f;                              // fp32 [P,64]
+    float* out_nchw; int n_valid;
+    int tiles_x;
+};
+
+template <int N>
+__global__ void __launch_bounds__(128) conv3x3_tc_kernel(const __grid_constant__ ConvParams p) {
+    constexpr int B_TAP = N * SR_CK * 2;               // bytes of one tap's [N][32] tile
+    constexpr int B_STAGE = 9 * B_TAP;
+    constexpr int STAGE = SR_A_STAGE + B_STAGE;
+    constexpr int TCOLS = (N < 32) ? 32 : N;
+    extern __shared__ __align__(1024) unsigned char smem[];
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + 2 * STAGE);      // [2] MMA-done per stage
+    uint32_t* tslot = reinterpret_cast<uint32_t*>(smem + 2 * STAGE + 16);
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int ty = blockIdx.x / p.tiles_x, tx = blockIdx.x - ty * p.tiles_x;
+    const int y0 = ty * SR_TY, x0 = tx * SR_TX;
+
+    if (tid == 0) {
+        sr_mbar_init(mbar + 0, 1); sr_mbar_init(mbar + 1, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" :: "r"(sr_s32(tslot)), "r"((uint32_t)TCOLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    const uint32_t tbase = *tslot;
+
+    const int sH = p.upsample ? (p.H >> 1) : p.H, sW = p.upsample ? (p.W >> 1) : p.W;
+    const int nchunks = p.cin / SR_CK;
+
+    auto load_stage = [&](int c, int st) {
+        unsigned char* A = smem + st * STAGE;
+        unsigned char* B = A + SR_A_STAGE;
+        // halo: 180 pixels x 4 planes of 16 B
+        for (int i = tid; i < SR_HY * SR_HX * 4; i += 128) {
+            const int plane = i & 3, pix = i >> 2;
+            const int hy = pix / SR_HX, hx = pix - hy * SR_HX;
+            const int gy = y0 - 1 + hy, gx = x0 - 1 + hx;
+            const bool in = (gy >= 0) & (gy < p.H) & (gx >= 0) & (gx < p.W);
+            const int sy = p.upsample ? (gy >> 1) : gy, sx = p.upsample ? (gx >> 1) : gx;
+            const __half* src = p.src;
+            if (in) src = p.src + ((size_t)sy * sW + sx) * p.src_cstride + p.src_c0 + c * SR_CK + plane * 8;
+            cp_async16(A + plane * SR_PLANE + hy * SR_ROW + hx * 16, src, in ? 16 : 0);
+        }
+        const unsigned char* wsrc = p.wpack + (size_t)c * B_STAGE;
+        for (int i = tid; i < B_STAGE / 16; i += 128) cp_async16(B + i * 16, wsrc + i * 16, 16);
+        asm volatile("cp.async.commit_group;\n" ::: "memory");
+        (void)sH;
+    };
+
+    load_stage(0, 0);
+    uint32_t ph[2] = {0, 0};
+    for (int c = 0; c < nchunks; ++c) {
+        const int st = c & 1;
+        if (c + 1 < nchunks) {
+            if (c >= 1) { sr_mbar_wait(mbar + (st ^ 1), ph[st ^ 1]); ph[st ^ 1] ^= 1; }   // MMAs of slice c-1 are done with that stage
+            load_stage(c + 1, st ^ 1);
+            asm volatile("cp.async.wait_group 1;\n" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+        }
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+        __syncthreads();
+        if (tid == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+            const uint32_t a0 = sr_s32(smem + st * STAGE), b0 = a0 + SR_A_STAGE;
+            const uint32_t idesc = sr_idesc(128, N < 16 ? 16 : N);
+#pragma unroll
+            for (int t = 0; t < 9; ++t) {
+                const int dy = t / 3, dx = t - dy * 3;
+#pragma unroll
+                for (int s = 0; s < SR_CK / 16; ++s) {
+                    const uint64_t ad = sr_desc(a0 + (2 * s) * SR_PLANE + dy * SR_ROW + dx * 16, SR_PLANE, SR_ROW);
+                    const uint64_t bd = sr_desc(b0 + t * B_TAP + s * 256, 128, (SR_CK / 8) * 128);
+                    sr_mma_ss(tbase, ad, bd, idesc, (c | t | s) != 0);
+                }
+            }
+            sr_commit(mbar + st);
+        }
+    }
+    {   // all MMAs done: the last commit covers everything issued before it
+        const int st = (nchunks - 1) & 1;
+        sr_mbar_wait(mbar + st, ph[st]);
+    }
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+
+    // ---------------- epilogue: thread r = y*8 + x owns one output pixel ----------------
+    const int py = y0 + (tid >> 3), px = x0 + (tid & 7);
+    const bool inside = (py < p.H) & (px < p.W);
+    const size_t pix = (size_t)py * p.W + px;
+    const uint32_t tl = tbase + ((uint32_t)(warp * 32) << 16);
+#pragma unroll
+    for (int c16 = 0; c16 < (N < 16 ? 16 : N) / 16; ++c16) {
+        uint32_t v[16];
+        sr_ld16(tl + c16 * 16, v);
+        asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+        if (!inside) continue;
+        float o[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) o[j] = __uint_as_float(v[j]) + __ldg(p.bias + c16 * 16 + j);
+        if (p.mode == SRM_STORE_F16) {
+            if (p.lrelu > 0.f) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) o[j] = o[j] > 0.f ? o[j] : o[j] * p.lrelu;
+            }
+            __half2 h[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) h[j] = __floats2half2_rn(o[2 * j], o[2 * j + 1]);
+            uint4* d = reinterpret_cast<uint4*>(p.dst_h + pix * p.dst_cstride + p.dst_c0 + c16 * 16);
+            d[0] = *reinterpret_cast<uint4*>(&h[0]);
+            d[1] = *reinterpret_cast<uint4*>(&h[4]);
+        } else if (p.mode == SRM_TRUNK) {
+            const float4* a = reinterpret_cast<const float4*>(p.add_f + pix * 64 + c16 * 16);
+            float4* d = reinterpret_cast<float4*>(p.dst_f + pix * 64 + c16 * 16);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float4 r = a[q];
+                d[q] = make_float4(o[4 * q] * p.scale + r.x, o[4 * q + 1] * p.scale + r.y, o[4 * q + 2] * p.scale + r.z, o[4 * q + 3] * p.scale + r.w);
+            }
+        } else if (p.mode == SRM_ADD_STORE_F16) {
+            const float4* a = reinterpret_cast<const float4*>(p.add_f + pix * 64 + c16 * 16);
+            __half2 h[8];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float4 r = a[q];
+                h[2 * q] = __floats2half2_rn(o[4 * q] + r.x, o[4 * q + 1] + r.y);
+                h[2 * q + 1] = __floats2half2_rn(o[4 * q + 2] + r.z, o[4 * q + 3] + r.w);
+            }
+            uint4* d = reinterpret_cast<uint4*>(p.dst_h + pix * p.dst_cstride + p.dst_c0 + c16 * 16);
+            d[0] = *reinterpret_cast<uint4*>(&h[0]);
+            d[1] = *reinterpret_cast<uint4*>(&h[4]);
+        } else if (p.mode == SRM_STORE_F32F16) {
+            float4* d = reinterpret_cast<float4*>(p.dst_f + pix * 64 + c16 * 16);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) d[q] = make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+        } else {  // SRM_OUT_NCHW
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+                if (c16 * 16 + j < p.n_valid) p.out_nchw[(size_t)(c16 * 16 + j) * p.H * p.W + pix] = o[j];
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" :: "r"(tbase), "r"((uint32_t)TCOLS) : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------
+// SFT layer: scale = C1s(lrelu(C0s(cond))), shift = C1h(lrelu(C0h(cond))), y = x*(scale+1)+shift
+// ---------------------------------------------------------------------------------------------
+struct SftParams {
+    const float* cond;               // [P,32] fp32
+    const float* w;                  // packed: s0 [32][32], s0b[32], h0 [32][32], h0b[32], s1 [COUT][32], s1b, h1 [COUT][32], h1b
+    const float* x_f; const __half* x_h; int xh_cstride, xh_c0;     // input: fp32 [P,64] or fp16 channel range
+    __half* dst_h; int dst_cstride, dst_c0;                          // fp16 output (or nullptr)
+    float* dst_f; const float* res_f; float res_scale;               // fp32 output: y*res_scale + res_f (RRDB tail) when dst_f != nullptr
+    long long P;
+};
+
+template <int COUT>
+__global__ void __launch_bounds__(128) sft_kernel(const __grid_constant__ SftParams p) {
+    constexpr int NW = 2 * (32 * 32 + 32) + 2 * (COUT * 32 + COUT);
+    extern __shared__ __align__(16) float sw[];
+    for (int i = threadIdx.x; i < NW; i += blockDim.x) sw[i] = __ldg(p.w + i);
+    __syncthreads();
+    const float* s0 = sw;             const float* s0b = s0 + 1024;
+    const float* h0 = s0b + 32;       const float* h0b = h0 + 1024;
+    const float* s1 = h0b + 32;       const float* s1b = s1 + COUT * 32;
+    const float* h1 = s1b + COUT;     const float* h1b = h1 + COUT * 32;
+    const long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pix >= p.P) return;
+    float c[32], ts[32], th[32];
+    const float4* cp = reinterpret_cast<const float4*>(p.cond + pix * 32);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) { const float4 v = __ldg(cp + q); c[4 * q] = v.x; c[4 * q + 1] = v.y; c[4 * q + 2] = v.z; c[4 * q + 3] = v.w; }
+#pragma unroll 4
+    for (int o = 0; o < 32; ++o) {
+        float a = s0b[o], b = h0b[o];
+#pragma unroll
+        for (int k = 0; k < 32; ++k) { a = fmaf(s0[o * 32 + k], c[k], a); b = fmaf(h0[o * 32 + k], c[k], b); }
+        ts[o] = a > 0.f ? a : 0.2f * a;
+        th[o] = b > 0.f ? b : 0.2f * b;
+    }
+#pragma unroll 1
+    for (int o0 = 0; o0 < COUT; o0 += 8) {
+        float y[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int o = o0 + j;
+            float sc = s1b[o], sh = h1b[o];
+#pragma unroll
+            for (int k = 0; k < 32; ++k) { sc = fmaf(s1[o * 32 + k], ts[k], sc); sh = fmaf(h1[o * 32 + k], th[k], sh); }
+            float x;
+            if (p.x_f) x = __ldg(p.x_f + pix * 64 + o);
+            else x = __half2float(p.x_h[pix * p.xh_cstride + p.xh_c0 + o]);
+            y[j] = x * (sc + 1.f) + sh;
+        }
+        if (p.dst_f) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) p.dst_f[pix * 64 + o0 + j] = y[j] * p.res_scale + __ldg(p.res_f + pix * 64 + o0 + j);
+        } else {
+            __half2 h[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) h[j] = __floats2half2_rn(y[2 * j], y[2 * j + 1]);
+            *reinterpret_cast<uint4*>(p.dst_h + pix * p.dst_cstride + p.dst_c0 + o0) = *reinterpret_cast<uint4*>(h);
+        }
+    }
+}
+
+// CondNet: conv3x3(1->64) lrelu, 1x1 64->64 lrelu, 1x1 64->64 lrelu, 1x1 64->32   (lib/sr_esrnet.py:440-444)
+struct CondParams { const float* cond_in; const float* w; float* cond_out; int H, W; };   // w: c0 [64][9], b0[64], c2 [64][64], b2, c4 [64][64], b4, c6 [32][64], b6
+
+__global__ void __launch_bounds__(128) condnet_kernel(const __grid_constant__ CondParams p) {
+    constexpr int NW = 64 * 9 + 64 + 2 * (64 * 64 + 64) + 32 * 64 + 32;
+    extern __shared__ __align__(16) float sw[];
+    for (int i = threadIdx.x; i < NW; i += blockDim.x) sw[i] = __ldg(p.w + i);
+    __syncthreads();
+    const float* c0 = sw; const float* b0 = c0 + 576; const float* c2 = b0 + 64; const float* b2 = c2 + 4096;
+    const float* c4 = b2 + 64; const float* b4 = c4 + 4096; const float* c6 = b4 + 64; const float* b6 = c6 + 2048;
+    const long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pix >= (long long)p.H * p.W) return;
+    const int y = (int)(pix / p.W), x = (int)(pix - (long long)y * p.W);
+    float n[9];
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx) {
+            const int yy = y + dy - 1, xx = x + dx - 1;
+            n[dy * 3 + dx] = (yy >= 0 && yy < p.H && xx >= 0 && xx < p.W) ? __ldg(p.cond_in + (size_t)yy * p.W + xx) : 0.f;
+        }
+    float a[64], b[64];
+#pragma unroll 4
+    for (int o = 0; o < 64; ++o) {
+        float v = b0[o];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) v = fmaf(c0[o * 9 + k], n[k], v);
+        a[o] = v > 0.f ? v : 0.2f * v;
+    }
+#pragma unroll 2
+    for (int o = 0; o < 64; ++o) {
+        float v = b2[o];
+#pragma unroll
+        for (int k = 0; k < 64; ++k) v = fmaf(c2[o * 64 + k], a[k], v);
+        b[o] = v > 0.f ? v : 0.2f * v;
+    }
+#pragma unroll 2
+    for (int o = 0; o < 64; ++o) {
+        float v = b4[o];
+#pragma unroll
+        for (int k = 0; k < 64; ++k) v = fmaf(c4[o * 64 + k], b[k], v);
+        a[o] = v > 0.f ? v : 0.2f * v;
+    }
+#pragma unroll 2
+    for (int o = 0; o < 32; ++o) {
+        float v = b6[o];
+#pragma unroll
+        for (int k = 0; k < 64; ++k) v = fmaf(c6[o * 64 + k], a[k], v);
+        p.cond_out[pix * 32 + o] = v;
+    }
+}
+
+// planar fp32 [C,H,W] -> NHWC fp16 [H,W,32] (zero padded)
+__global__ void nchw_to_nhwc32_kernel(const float* __restrict__ src, __half* __restrict__ dst, int C, long long P) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P * 32) return;
+    const long long pix = i >> 5;
+    const int c = (int)(i & 31);
+    dst[i] = __float2half_rn(c < C ? src[(size_t)c * P + pix] : 0.f);
+}
+
+// conv weight [Cout][Cin][3][3] fp32 -> [cin_slice][tap][NPAD][32] canonical K-major fp16 tiles
+__global__ void pack_conv3x3_kernel(const float* __restrict__ W, unsigned char* __restrict__ dst,
+                                    int cout, int cin, int npad, int nslices) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = (long long)nslices * 9 * npad * 32;
+    if (i >= total) return;
+    const int k = (int)(i & 31);
+    long long r = i >> 5;
+    const int n = (int)(r % npad); r /= npad;
+    const int t = (int)(r % 9);
+    const int sl = (int)(r / 9);
+    const int ci = sl * 32 + k;
+    const float w = (n < cout && ci < cin) ? W[((size_t)n * cin + ci) * 9 + t] : 0.f;
+    const size_t off = ((size_t)sl * 9 + t) * (npad * 64) + tc_canon_off(n, k >> 3, 4) + (k & 7) * 2;
+    *reinterpret_cast<__half*>(dst + off) = __float2half_rn(w);
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+struct SrConv { unsigned char* wpack; float* bias; int cin_pad, cout, npad; };
+struct SrSft { float* w; int cout; };
+
+struct k4_srnet {
+    int num_feat, num_block, num_grow, num_cond, n_in, scale;
+    SrConv conv_first, conv_body, conv_up1, conv_up2, conv_hr, conv_last;
+    SrConv rdb_conv[32][3][5];
+    SrSft rdb_sft[32][3][2];
+    SrSft rrdb_sft[32];
+    SrSft sftbody;
+    float* condnet_w;
+    void* allocs[1024];
+    int n_allocs;
+    size_t bytes;
+};
+
+namespace {
+
+int sr_alloc(k4_srnet* n, void** p, size_t bytes) {
+    if (n->n_allocs >= 1024) return K4_ERR_INVALID_ARG;
+    K4_CUDA_TRY(cudaMalloc(p, bytes ? bytes : 16));
+    n->allocs[n->n_allocs++] = *p;
+    n->bytes += bytes;
+    return K4_OK;
+}
+
+int make_conv(k4_srnet* n, SrConv& c, const float* w, const float* b, int cout, int cin, cudaStream_t s) {
+    c.cout = cout;
+    c.npad = cout <= 16 ? 16 : (cout <= 32 ? 32 : 64);
+    c.cin_pad = (cin + 31) / 32 * 32;
+    const int nsl = c.cin_pad / 32;
+    const size_t bytes = (size_t)nsl * 9 * c.npad * 64;
+    int st = sr_alloc(n, (void**)&c.wpack, bytes);
+    if (st) return st;
+    st = sr_alloc(n, (void**)&c.bias, 64 * 4);
+    if (st) return st;
+    K4_CUDA_TRY(cudaMemsetAsync(c.bias, 0, 64 * 4, s));
+    K4_CUDA_TRY(cudaMemcpyAsync(c.bias, b, (size_t)cout * 4, cudaMemcpyDeviceToDevice, s));
+    const long long total = (long long)nsl * 9 * c.npad * 32;
+    pack_conv3x3_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(w, c.wpack, cout, cin, c.npad, nsl);
+    K4_CUDA_TRY(cudaGetLastError());
+    return K4_OK;
+}
+
+// SFT weights: 4 convs in the order scale0, scale1, shift0, shift1 (weight, bias each) -> packed s0,s0b,h0,h0b,s1,s1b,h1,h1b
+int make_sft(k4_srnet* n, SrSft& f, const float* const* pw, int cout, cudaStream_t s) {
+    f.cout = cout;
+    const size_t nw = 2 * (1024 + 32) + 2 * ((size_t)cout * 32 + cout);
+    int st = sr_alloc(n, (void**)&f.w, nw * 4);
+    if (st) return st;
+    float* d = f.w;
+    auto cp = [&](const float* src, size_t cnt) { cudaMemcpyAsync(d, src, cnt * 4, cudaMemcpyDeviceToDevice, s); d += cnt; };
+    cp(pw[0], 1024); cp(pw[1], 32);                 // scale_conv0 w, b
+    cp(pw[4], 1024); cp(pw[5], 32);                 // shift_conv0 w, b
+    cp(pw[2], (size_t)cout * 32); cp(pw[3], cout);  // scale_conv1 w, b
+    cp(pw[6], (size_t)cout * 32); cp(pw[7], cout);  // shift_conv1 w, b
+    K4_CUDA_TRY(cudaGetLastError());
+    return K4_OK;
+}
+
+template <int N>
+int launch_conv(const ConvParams& p, cudaStream_t s) {
+    constexpr int STAGE = SR_A_STAGE + 9 * N * SR_CK * 2;
+    constexpr int SMEM = 2 * STAGE + 64;
+    static bool attr_set = false;
+    if (!attr_set) {
+        K4_CUDA_TRY(cudaFuncSetAttribute(conv3x3_tc_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+        attr_set = true;
+    }
+    const int tiles_y = (p.H + SR_TY - 1) / SR_TY;
+    conv3x3_tc_kernel<N><<<(unsigned)(p.tiles_x * tiles_y), 128, SMEM, s>>>(p);
+    K4_CUDA_TRY(cudaGetLastError());
+    return K4_OK;
+}
+
+int run_conv(const SrConv& c, ConvParams p, cudaStream_t s) {
+    p.wpack = c.wpack; p.bias = c.bias; p.cin = c.cin_pad;
+    p.tiles_x = (p.W + SR_TX - 1) / SR_TX;
+    if (c.npad == 64) return launch_conv<64>(p, s);
+    if (c.npad == 32) return launch_conv<32>(p, s);
+    return launch_conv<16>(p, s);
+}
+
+template <int COUT>
+int launch_sft(const SftParams& p, cudaStream_t s) {
+    constexpr int NW = 2 * (32 * 32 + 32) + 2 * (COUT * 32 + COUT);
+    sft_kernel<COUT><<<(unsigned)((p.P + 127) / 128), 128, NW * 4, s>>>(p);
+    K4_CUDA_TRY(cudaGetLastError());
+    return K4_OK;
+}
+
+int run_sft(const SrSft& f, SftParams p, cudaStream_t s) {
+    p.w = f.w;
+    return f.cout == 64 ? launch_sft<64>(p, s) : launch_sft<32>(p, s);
+}
+
+}  // namespace
+
+extern "C" int k4_srnet_destroy(k4_srnet* n) {
+    if (!n) return K4_OK;
+    for (int i = 0; i < n->n_allocs; ++i) cudaFree(n->allocs[i]);
+    delete n;
+    return K4_OK;
+}
+
+extern "C" int k4_srnet_create(const k4_srnet_desc* d, k4_stream_t stream, k4_srnet** out) {
+    if (!d || !out || !d->h_params) return K4_ERR_INVALID_ARG;
+    *out = nullptr;
+    if (d->num_feat != 64 || d->num_grow_ch != 32 || d->num_cond != 1 || d->n_in_colors != 3 || d->scale != 4 ||
+        d->num_block < 1 || d->num_block > 32)
+        return K4_ERR_UNSUPPORTED;          // the shipped configuration (run_sr.py:1353); others are not built
+    const int expect = 2 * (1 + 4 + d->num_block * (3 * 13 + 4) + 4 + 5);
+    if (d->n_params != expect) return K4_ERR_INVALID_ARG;
+    for (int i = 0; i < d->n_params; ++i) if (!d->h_params[i]) return K4_ERR_INVALID_ARG;
+    int st = k4_device_check();
+    if (st != K4_OK) return st;
+    cudaStream_t s = (cudaStream_t)stream;
+    k4_srnet* n = new (std::nothrow) k4_srnet();
+    if (!n) return K4_ERR_INVALID_ARG;
+    memset(n, 0, sizeof(*n));
+    n->num_feat = 64; n->num_block = d->num_block; n->num_grow = 32; n->num_cond = 1; n->n_in = 3; n->scale = 4;
+    const float* const* P = d->h_params;
+    int k = 0;
+#define SR_TRY(x) do { st = (x); if (st != K4_OK) { k4_srnet_destroy(n); return st; } } while (0)
+    SR_TRY(make_conv(n, n->conv_first, P[k], P[k + 1], 64, 3, s)); k += 2;
+    {   // CondNet.0 (64x1x3x3), .2 (64x64), .4 (64x64), .6 (32x64)
+        const size_t nw = 64 * 9 + 64 + 2 * (64 * 64 + 64) + 32 * 64 + 32;
+        SR_TRY(sr_alloc(n, (void**)&n->condnet_w, nw * 4));
+        float* dd = n->condnet_w;
+        const size_t cnt[8] = {576, 64, 4096, 64, 4096, 64, 2048, 32};
+        for (int q = 0; q < 8; ++q) { cudaMemcpyAsync(dd, P[k + q], cnt[q] * 4, cudaMemcpyDeviceToDevice, s); dd += cnt[q]; }
+        k += 8;
+    }
+    for (int i = 0; i < d->num_block; ++i) {
+        for (int j = 0; j < 3; ++j) {
+            for (int c = 0; c < 5; ++c) {
+                const int cin = 64 + 32 * c, cout = (c == 4) ? 64 : 32;
+                SR_TRY(make_conv(n, n->rdb_conv[i][j][c], P[k], P[k + 1], cout, cin, s)); k += 2;
+            }
+            SR_TRY(make_sft(n, n->rdb_sft[i][j][0], P + k, 64, s)); k += 8;
+            SR_TRY(make_sft(n, n->rdb_sft[i][j][1], P + k, 32, s)); k += 8;
+        }
+        SR_TRY(make_sft(n, n->rrdb_sft[i], P + k, 64, s)); k += 8;
+    }
+    SR_TRY(make_sft(n, n->sftbody, P + k, 64, s)); k += 8;
+    SR_TRY(make_conv(n, n->conv_body, P[k], P[k + 1], 64, 64, s)); k += 2;
+    SR_TRY(make_conv(n, n->conv_up1, P[k], P[k + 1], 64, 64, s)); k += 2;
+    SR_TRY(make_conv(n, n->conv_up2, P[k], P[k + 1], 64, 64, s)); k += 2;
+    SR_TRY(make_conv(n, n->conv_hr, P[k], P[k + 1], 64, 64, s)); k += 2;
+    SR_TRY(make_conv(n, n->conv_last, P[k], P[k + 1], 3, 64, s)); k += 2;
+#undef SR_TRY
+    *out = n;
+    return K4_OK;
+}
+
+// workspace layout for an h x w tile (P = h*w LR pixels)
+struct SrWs { size_t in16, cond32, feat, trunkA, trunkB, cat, sbody, bf, up1, up2, hr, total; };
+static SrWs sr_ws(int h, int w) {
+    const size_t P = (size_t)h * w;
+    SrWs o; size_t off = 0;
+    auto take = [&](size_t b) { size_t r = off; off += (b + 255) & ~(size_t)255; return r; };
+    o.in16 = take(P * 32 * 2); o.cond32 = take(P * 32 * 4); o.feat = take(P * 64 * 4);
+    o.trunkA = take(P * 64 * 4); o.trunkB = take(P * 64 * 4); o.cat = take(P * 192 * 2);
+    o.sbody = take(P * 64 * 2); o.bf = take(P * 64 * 2);
+    o.up1 = take(P * 4 * 64 * 2); o.up2 = take(P * 16 * 64 * 2); o.hr = take(P * 16 * 64 * 2);
+    o.total = off;
+    return o;
+}
+
+extern "C" size_t k4_srnet_workspace_bytes(const k4_srnet*, int32_t h, int32_t w) {
+    if (h <= 0 || w <= 0) return 0;
+    return sr_ws(h, w).total;
+}
+
+extern "C" int k4_srnet_forward(const k4_srnet* n, const float* d_x, const float* d_cond, int32_t h, int32_t w,
+                                float* d_out, void* d_ws, size_t ws_bytes, k4_stream_t stream) {
+    if (!n || !d_x || !d_cond || !d_out || h <= 0 || w <= 0) return K4_ERR_INVALID_ARG;
+    const SrWs L = sr_ws(h, w);
+    if (!d_ws || ws_bytes < L.total) return K4_ERR_WORKSPACE;
+    cudaStream_t s = (cudaStream_t)stream;
+    unsigned char* ws = (unsigned char*)d_ws;
+    const long long P = (long long)h * w;
+    __half* in16 = (__half*)(ws + L.in16); float* cond32 = (float*)(ws + L.cond32); float* feat = (float*)(ws + L.feat);
+    float* tA = (float*)(ws + L.trunkA); float* tB = (float*)(ws + L.trunkB); __half* cat = (__half*)(ws + L.cat);
+    __half* sbody = (__half*)(ws + L.sbody); __half* bf = (__half*)(ws + L.bf);
+    __half* up1 = (__half*)(ws + L.up1); __half* up2 = (__half*)(ws + L.up2); __half* hr = (__half*)(ws + L.hr);
+    int st;
+#define SR_DO(x) do { st = (x); if (st != K4_OK) return st; } while (0)
+    nchw_to_nhwc32_kernel<<<(unsigned)((P * 32 + 255) / 256), 256, 0, s>>>(d_x, in16, 3, P);
+    K4_CUDA_TRY(cudaGetLastError());
+    {
+        CondParams cp{d_cond, n->condnet_w, cond32, h, w};
+        constexpr int NW = 64 * 9 + 64 + 2 * (64 * 64 + 64) + 32 * 64 + 32;
+        static bool set = false;
+        if (!set) { K4_CUDA_TRY(cudaFuncSetAttribute(condnet_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, NW * 4)); set = true; }
+        condnet_kernel<<<(unsigned)((P + 127) / 128), 128, NW * 4, s>>>(cp);
+        K4_CUDA_TRY(cudaGetLastError());
+    }
+    ConvParams c0{};
+    c0.H = h; c0.W = w;
+    {   // feat = conv_first(x): fp32 into `feat`, copy = initial trunk
+        ConvParams p = c0; p.src = in16; p.src_cstride = 32; p.src_c0 = 0; p.mode = SRM_STORE_F32F16; p.dst_f = feat;
+        SR_DO(run_conv(n->conv_first, p, s));
+        K4_CUDA_TRY(cudaMemcpyAsync(tA, feat, (size_t)P * 64 * 4, cudaMemcpyDeviceToDevice, s));
+    }
+    for (int i = 0; i < n->num_block; ++i) {
+        // RRDB_SFT.forward: trunk A holds x (kept for the block's tail), RDBs update A -> B -> B -> B
+        const float* cur = tA;
+        for (int j = 0; j < 3; ++j) {
+            {   // xc0 = sft0(x) -> cat[0:64]
+                SftParams sp{}; sp.cond = cond32; sp.x_f = cur; sp.dst_h = cat; sp.dst_cstride = 192; sp.dst_c0 = 0; sp.P = P;
+                SR_DO(run_sft(n->rdb_sft[i][j][0], sp, s));
+            }
+            for (int c = 0; c < 4; ++c) {   // x{c+1} = lrelu(conv(cat[0:64+32c])) -> cat[64+32c : 96+32c]
+                ConvParams p = c0; p.src = cat; p.src_cstride = 192; p.src_c0 = 0; p.mode = SRM_STORE_F16; p.lrelu = 0.2f;
+                p.dst_h = cat; p.dst_cstride = 192; p.dst_c0 = 64 + 32 * c;
+                SR_DO(run_conv(n->rdb_conv[i][j][c], p, s));
+            }
+            {   // xc1 = sft1(x4) in place: cat[160:192]
+                SftParams sp{}; sp.cond = cond32; sp.x_h = cat; sp.xh_cstride = 192; sp.xh_c0 = 160;
+                sp.dst_h = cat; sp.dst_cstride = 192; sp.dst_c0 = 160; sp.P = P;
+                SR_DO(run_sft(n->rdb_sft[i][j][1], sp, s));
+            }
+            {   // x = conv5(cat) * 0.2 + x
+                ConvParams p = c0; p.src = cat; p.src_cstride = 192; p.src_c0 = 0; p.mode = SRM_TRUNK; p.scale = 0.2f;
+                p.add_f = cur; p.dst_f = tB;
+                SR_DO(run_conv(n->rdb_conv[i][j][4], p, s));
+                cur = tB;
+            }
+        }
+        {   // out = sft0(rdb3 out) * 0.2 + x_in  -> A
+            SftParams sp{}; sp.cond = cond32; sp.x_f = tB; sp.dst_f = tA; sp.res_f = tA; sp.res_scale = 0.2f; sp.P = P;
+            SR_DO(run_sft(n->rrdb_sft[i], sp, s));
+        }
+    }
+    {   // body_feat = conv_body(sftbody(trunk)) + feat
+        SftParams sp{}; sp.cond = cond32; sp.x_f = tA; sp.dst_h = sbody; sp.dst_cstride = 64; sp.dst_c0 = 0; sp.P = P;
+        SR_DO(run_sft(n->sftbody, sp, s));
+        ConvParams p = c0; p.src = sbody; p.src_cstride = 64; p.mode = SRM_ADD_STORE_F16; p.add_f = feat; p.dst_h = bf; p.dst_cstride = 64;
+        SR_DO(run_conv(n->conv_body, p, s));
+    }
+    {   // upsample x2 (nearest) + conv + lrelu, twice; conv_hr + lrelu; conv_last
+        ConvParams p = c0; p.H = 2 * h; p.W = 2 * w; p.upsample = 1; p.src = bf; p.src_cstride = 64; p.mode = SRM_STORE_F16; p.lrelu = 0.2f;
+        p.dst_h = up1; p.dst_cstride = 64;
+        SR_DO(run_conv(n->conv_up1, p, s));
+        p.H = 4 * h; p.W = 4 * w; p.src = up1; p.dst_h = up2;
+        SR_DO(run_conv(n->conv_up2, p, s));
+        p.upsample = 0; p.src = up2; p.dst_h = hr;
+        SR_DO(run_conv(n->conv_hr, p, s));
+        ConvParams q = c0; q.H = 4 * h; q.W = 4 * w; q.src = hr; q.src_cstride = 64; q.mode = SRM_OUT_NCHW; q.out_nchw = d_out; q.n_valid = 3;
+        SR_DO(run_conv(n->conv_last, q, s));
+    }
+#undef SR_DO
+    return K4_OK;
+}

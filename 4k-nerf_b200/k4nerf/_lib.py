@@ -42,6 +42,14 @@ class RenderOut(C.Structure):
     ]
 
 
+class SrnetDesc(C.Structure):
+    _fields_ = [
+        ('n_in_colors', C.c_int32), ('scale', C.c_int32), ('num_feat', C.c_int32), ('num_block', C.c_int32),
+        ('num_grow_ch', C.c_int32), ('num_cond', C.c_int32), ('n_params', C.c_int32), ('reserved0', C.c_int32),
+        ('h_params', C.POINTER(C.c_void_p)),
+    ]
+
+
 EXPORTS = {
     'k4_abi_version': (C.c_int, []),
     'k4_status_string': (C.c_char_p, [C.c_int]),
@@ -53,6 +61,11 @@ EXPORTS = {
     'k4_render_workspace_bytes': (C.c_size_t, [C.c_void_p, C.c_int64]),
     'k4_render_rays': (C.c_int, [C.c_void_p, C.POINTER(RenderArgs), C.c_void_p, C.c_void_p, C.c_void_p,
                                  C.c_int64, C.POINTER(RenderOut), C.c_void_p, C.c_size_t, C.c_void_p]),
+    'k4_srnet_create': (C.c_int, [C.POINTER(SrnetDesc), C.c_void_p, C.POINTER(C.c_void_p)]),
+    'k4_srnet_destroy': (C.c_int, [C.c_void_p]),
+    'k4_srnet_workspace_bytes': (C.c_size_t, [C.c_void_p, C.c_int32, C.c_int32]),
+    'k4_srnet_forward': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
+                                   C.c_size_t, C.c_void_p]),
     'k4_make_rays': (C.c_int, [C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_int32, C.c_int32, C.c_int32,
                                C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
 }

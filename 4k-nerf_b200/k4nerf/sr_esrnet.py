@@ -1,0 +1,185 @@
+"""SFTNet (the VC-Decoder) with the reference's constructor, parameter names and call contract
+(lib/sr_esrnet.py:400-527), executed by the tcgen05 convolution pipeline of libk4nerf.so
+(csrc/k4_sr.cu).  The module tree below only OWNS the parameters (so reference checkpoints and
+``pretrained/RealESRNet_x4plus.pth`` load with the same keys, ``strict=False`` as run_sr.py:663);
+no torch op runs in ``forward``."""
+import ctypes as C
+import math
+from copy import deepcopy
+
+import torch
+from torch import nn
+
+from . import _lib
+from ._scene import require_cuda
+
+
+class SFTLayer(nn.Module):
+    def __init__(self, num_feat=64, num_grow_ch=32):
+        super().__init__()
+        self.SFT_scale_conv0 = nn.Conv2d(num_grow_ch, num_grow_ch, 1)
+        self.SFT_scale_conv1 = nn.Conv2d(num_grow_ch, num_feat, 1)
+        self.SFT_shift_conv0 = nn.Conv2d(num_grow_ch, num_grow_ch, 1)
+        self.SFT_shift_conv1 = nn.Conv2d(num_grow_ch, num_feat, 1)
+
+    def convs(self):
+        return [self.SFT_scale_conv0, self.SFT_scale_conv1, self.SFT_shift_conv0, self.SFT_shift_conv1]
+
+
+class ResidualDenseBlock_SFT(nn.Module):
+    def __init__(self, num_feat=64, num_grow_ch=32):
+        super().__init__()
+        self.conv1 = nn.Conv2d(num_feat, num_grow_ch, 3, 1, 1)
+        self.conv2 = nn.Conv2d(num_feat + num_grow_ch, num_grow_ch, 3, 1, 1)
+        self.conv3 = nn.Conv2d(num_feat + 2 * num_grow_ch, num_grow_ch, 3, 1, 1)
+        self.conv4 = nn.Conv2d(num_feat + 3 * num_grow_ch, num_grow_ch, 3, 1, 1)
+        self.conv5 = nn.Conv2d(num_feat + 4 * num_grow_ch, num_feat, 3, 1, 1)
+        self.sft0 = SFTLayer(num_feat, num_grow_ch)
+        self.sft1 = SFTLayer(num_grow_ch, num_grow_ch)
+        for c in (self.conv1, self.conv2, self.conv3, self.conv4, self.conv5):   # default_init_weights(..., 0.1)
+            nn.init.kaiming_normal_(c.weight)
+            c.weight.data *= 0.1
+            c.bias.data.zero_()
+
+
+class RRDB_SFT(nn.Module):
+    def __init__(self, num_feat, num_grow_ch=32):
+        super().__init__()
+        self.rdb1 = ResidualDenseBlock_SFT(num_feat, num_grow_ch)
+        self.rdb2 = ResidualDenseBlock_SFT(num_feat, num_grow_ch)
+        self.rdb3 = ResidualDenseBlock_SFT(num_feat, num_grow_ch)
+        self.sft0 = SFTLayer(num_feat, num_grow_ch)
+
+
+class _NetHandle:
+    def __init__(self, ptr, fingerprint):
+        self.ptr, self.fingerprint = ptr, fingerprint
+
+    def __del__(self):
+        try:
+            if self.ptr:
+                _lib.lib.k4_srnet_destroy(self.ptr)
+                self.ptr = None
+        except Exception:
+            pass
+
+
+class SFTNet(nn.Module):
+    def __init__(self, n_in_colors, scale, num_feat=64, num_block=5, num_grow_ch=32, num_cond=1, dswise=False):
+        super().__init__()
+        if dswise or n_in_colors != 3 or scale != 4 or num_feat != 64 or num_grow_ch != 32 or num_cond != 1:
+            raise NotImplementedError('k4nerf builds the shipped VC-Decoder: SFTNet(3, 4, 64, n, 32, 1) (run_sr.py:1353)')
+        self.scale = scale
+        self.dswise = dswise
+        self.conv_first = nn.Conv2d(n_in_colors, num_feat, 3, 1, 1)
+        self.body = nn.Sequential(*[RRDB_SFT(num_feat=num_feat, num_grow_ch=num_grow_ch) for _ in range(num_block)])
+        self.conv_body = nn.Conv2d(num_feat, num_feat, 3, 1, 1)
+        self.conv_up1 = nn.Conv2d(num_feat, num_feat, 3, 1, 1)
+        self.conv_up2 = nn.Conv2d(num_feat, num_feat, 3, 1, 1)
+        self.conv_hr = nn.Conv2d(num_feat, num_feat, 3, 1, 1)
+        self.conv_last = nn.Conv2d(num_feat, 3, 3, 1, 1)
+        self.sftbody = SFTLayer(num_feat, num_grow_ch)
+        self.CondNet = nn.Sequential(
+            nn.Conv2d(num_cond, 64, 3, 1, 1), nn.LeakyReLU(0.2, True),
+            nn.Conv2d(64, 64, 1), nn.LeakyReLU(0.2, True),
+            nn.Conv2d(64, 64, 1), nn.LeakyReLU(0.2, True),
+            nn.Conv2d(64, 32, 1))
+        self._cfg = (n_in_colors, scale, num_feat, num_block, num_grow_ch, num_cond)
+
+    # -- parameter order of include/k4nerf.h (k4_srnet_desc) ---------------------------------------
+    def _ordered_convs(self):
+        cs = [self.conv_first, self.CondNet[0], self.CondNet[2], self.CondNet[4], self.CondNet[6]]
+        for blk in self.body:
+            for rdb in (blk.rdb1, blk.rdb2, blk.rdb3):
+                cs += [rdb.conv1, rdb.conv2, rdb.conv3, rdb.conv4, rdb.conv5] + rdb.sft0.convs() + rdb.sft1.convs()
+            cs += blk.sft0.convs()
+        cs += self.sftbody.convs() + [self.conv_body, self.conv_up1, self.conv_up2, self.conv_hr, self.conv_last]
+        return cs
+
+    def _get_net(self):
+        params = [t for c in self._ordered_convs() for t in (c.weight, c.bias)]
+        fp = tuple((t.data_ptr(), t._version) for t in params)
+        h = getattr(self, '_k4_net', None)
+        if h is not None and h.fingerprint == fp:
+            return h
+        require_cuda(*params)
+        dev = params[0].device
+        keep = [t.detach().to(torch.float32).contiguous() for t in params]
+        arr = (C.c_void_p * len(keep))(*[t.data_ptr() for t in keep])
+        d = _lib.SrnetDesc()
+        d.n_in_colors, d.scale, d.num_feat, d.num_block, d.num_grow_ch, d.num_cond = self._cfg
+        d.n_params = len(keep)
+        d.h_params = C.cast(arr, C.POINTER(C.c_void_p))
+        out = C.c_void_p()
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev)
+            _lib.check(_lib.lib.k4_srnet_create(C.byref(d), C.c_void_p(stream.cuda_stream), C.byref(out)), 'k4_srnet_create')
+            stream.synchronize()
+        h = _NetHandle(out.value, fp)
+        object.__setattr__(self, '_k4_net', h)
+        return h
+
+    @torch.no_grad()
+    def forward(self, x, cond, fea=None):
+        """x [1,3,h,w], cond [1,1,h,w] (CUDA, fp32) -> [1,3,4h,4w]  (lib/sr_esrnet.py:446-465)."""
+        if fea is not None:
+            raise NotImplementedError('the `fea` branch needs conv_prefea (n_in_colors > 3), not in the shipped config')
+        require_cuda(x, cond)
+        assert x.dim() == 4 and x.shape[0] == 1 and x.shape[1] == 3 and cond.shape[1] == 1, 'batch 1, 3+1 channels'
+        h, w = int(x.shape[2]), int(x.shape[3])
+        net = self._get_net()
+        dev = x.device
+        x = x.to(torch.float32).contiguous()
+        cond = cond.to(torch.float32).contiguous()
+        out = torch.empty((1, 3, h * self.scale, w * self.scale), device=dev, dtype=torch.float32)
+        nbytes = int(_lib.lib.k4_srnet_workspace_bytes(net.ptr, h, w))
+        ws = getattr(self, '_k4_ws', None)
+        if ws is None or ws.numel() < nbytes or ws.device != dev:
+            ws = torch.empty(nbytes, device=dev, dtype=torch.uint8)
+            object.__setattr__(self, '_k4_ws', ws)
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            _lib.check(_lib.lib.k4_srnet_forward(net.ptr, x.data_ptr(), cond.data_ptr(), h, w, out.data_ptr(),
+                                                 ws.data_ptr(), ws.numel(), C.c_void_p(stream)), 'k4_srnet_forward')
+        return out
+
+    @torch.no_grad()
+    def tile_process(self, img, cond, tile_size, tile_pad=10, to_cpu=True):
+        """SFTNet.tile_process (lib/sr_esrnet.py:467-527): same tile geometry (the 10-pixel pad is far
+        smaller than the receptive field, so the tiling is part of the result); the output is
+        assembled on the device and moved to the CPU once (the reference copies every tile)."""
+        batch, channel, height, width = img.shape
+        cond = cond.unsqueeze(0)
+        s = self.scale
+        output = img.new_zeros((batch, channel, height * s, width * s))
+        tiles_x = math.ceil(width / tile_size)
+        tiles_y = math.ceil(height / tile_size)
+        for y in range(tiles_y):
+            for x in range(tiles_x):
+                x0, y0 = x * tile_size, y * tile_size
+                x1, y1 = min(x0 + tile_size, width), min(y0 + tile_size, height)
+                x0p, x1p = max(x0 - tile_pad, 0), min(x1 + tile_pad, width)
+                y0p, y1p = max(y0 - tile_pad, 0), min(y1 + tile_pad, height)
+                out_tile = self(img[:, :, y0p:y1p, x0p:x1p], cond[:, :, y0p:y1p, x0p:x1p])
+                ty, tx = (y0 - y0p) * s, (x0 - x0p) * s
+                output[:, :, y0 * s:y1 * s, x0 * s:x1 * s] = out_tile[:, :, ty:ty + (y1 - y0) * s, tx:tx + (x1 - x0) * s]
+        return output.to('cpu') if to_cpu else output
+
+    def load_network(self, load_path, device, strict=True, param_key='params_ema'):
+        """lib/sr_esrnet.py:529-554 (keys may carry a 'module.' prefix; mismatching sizes are skipped
+        when strict=False)."""
+        load_net = torch.load(load_path, map_location=device, weights_only=False)
+        if param_key is not None:
+            if param_key not in load_net and 'params' in load_net:
+                param_key = 'params'
+            load_net = load_net[param_key]
+        for k, v in deepcopy(load_net).items():
+            if k.startswith('module.'):
+                load_net[k[7:]] = v
+                load_net.pop(k)
+        if not strict:
+            cur = self.state_dict()
+            for k in list(load_net):
+                if k in cur and cur[k].size() != load_net[k].size():
+                    load_net[k + '.ignore'] = load_net.pop(k)
+        self.load_state_dict(load_net, strict=strict)

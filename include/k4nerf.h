@@ -151,6 +151,38 @@ K4_API int k4_make_rays(const float* h_K, const float* h_c2w, int32_t H, int32_t
                  int32_t inverse_y, int32_t flip_x, int32_t flip_y,
                  float* d_rays_o, float* d_rays_d, float* d_viewdirs, k4_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * VC-Decoder: SFTNet (lib/sr_esrnet.py:400-465), the x4 SFT-RRDB upsampler that turns the marcher's
+ * rgb_feature + depth images into the 4K frame (run_sr.py:1353-1387).
+ *
+ * h_params: HOST array of DEVICE pointers to the fp32 parameters (weight, bias alternating) of the
+ * 229 convolutions in this fixed order -- the reference module's registration order:
+ *   conv_first; CondNet.0, CondNet.2, CondNet.4, CondNet.6;
+ *   for i in blocks: for j in rdb1..rdb3: conv1..conv5,
+ *                                          sft0.{SFT_scale_conv0, SFT_scale_conv1, SFT_shift_conv0, SFT_shift_conv1},
+ *                                          sft1.{same four};
+ *                    body.i.sft0.{same four};
+ *   sftbody.{same four}; conv_body; conv_up1; conv_up2; conv_hr; conv_last.
+ * Only the shipped configuration SFTNet(n_in_colors=3, scale=4, num_feat=64, num_block<=32,
+ * num_grow_ch=32, num_cond=1, dswise=False) (run_sr.py:1353) is built; others return K4_ERR_UNSUPPORTED.
+ */
+typedef struct k4_srnet_desc {
+    int32_t n_in_colors, scale, num_feat, num_block, num_grow_ch, num_cond;
+    int32_t n_params;                  /* = 2 * number of convolutions */
+    int32_t reserved0;
+    const float* const* h_params;
+} k4_srnet_desc;
+
+K4_API int k4_srnet_create(const k4_srnet_desc* desc, k4_stream_t stream, k4_srnet** out_net);
+K4_API int k4_srnet_destroy(k4_srnet* net);
+K4_API size_t k4_srnet_workspace_bytes(const k4_srnet* net, int32_t h, int32_t w);
+
+/* Replaces: SFTNet.forward(x, cond) (lib/sr_esrnet.py:446-465) for one tile.
+ * d_x [3,h,w], d_cond [1,h,w] planar fp32 (the reference's NCHW, batch 1); d_out [3,4h,4w] fp32.
+ * Tiling (SFTNet.tile_process, lib/sr_esrnet.py:467-527) is host logic above this call. */
+K4_API int k4_srnet_forward(const k4_srnet* net, const float* d_x, const float* d_cond, int32_t h, int32_t w,
+                            float* d_out, void* d_workspace, size_t workspace_bytes, k4_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -84,3 +84,15 @@ def test_unsupported_grid_type_raises():
     with pytest.raises(NotImplementedError):
         k4nerf.DirectVoxGO([-1, -1, -1], [1, 1, 1], num_voxels=8 ** 3, num_voxels_base=8 ** 3, alpha_init=1e-2,
                            density_type='TensoRFGrid')
+
+
+def test_sftnet_state_dict_matches_reference_names():
+    from oracle import sftnet
+    n = k4nerf.SFTNet(3, 4, 64, 5, 32, 1)
+    sd = sftnet.random_state_dict(seed=3)           # names/shapes restated from lib/sr_esrnet.py:411-444
+    assert set(n.state_dict()) == set(sd)
+    for k, v in n.state_dict().items():
+        assert tuple(v.shape) == tuple(sd[k].shape), k
+    assert len(n._ordered_convs()) == 229            # 229 convs per forward
+    with pytest.raises(NotImplementedError):
+        k4nerf.SFTNet(3, 2, 64, 5, 32, 1)
