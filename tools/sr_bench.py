@@ -1,0 +1,54 @@
+"""VC-Decoder timing: k4nerf.SFTNet.tile_process (tcgen05 convs) vs the same network run through
+torch/cuDNN (the reference's execution path: oracle.sftnet on CUDA tensors), 1008x756 -> 4032x3024,
+tile 510 / pad 10 (run_sr.py --test_tile 510)."""
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, '4k-nerf_b200')):
+    sys.path.insert(0, p)
+import k4nerf  # noqa: E402
+from oracle import pipeline, sftnet  # noqa: E402
+
+
+def main():
+    dev = torch.device('cuda', 0)
+    H, W = (int(sys.argv[1]), int(sys.argv[2])) if len(sys.argv) > 2 else (756, 1008)
+    iters = 3
+    sd = sftnet.random_state_dict(seed=3, scale=1.0)
+    net = k4nerf.SFTNet(3, 4, 64, 5, 32, 1)
+    net.load_state_dict(sd)
+    net = net.to(dev)
+    g = torch.Generator().manual_seed(1)
+    img = torch.rand(1, 3, H, W, generator=g).to(dev)
+    cond = torch.rand(1, H, W, generator=g).to(dev)
+    flop = 2 * 5188864 * sum((p[1] - p[0]) * (p[3] - p[2]) for p in sftnet.tile_plan(H, W, 510, 10))
+
+    def timeit(fn):
+        fn(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            out = fn()
+        e1.record(); torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters, out
+
+    ms, out = timeit(lambda: net.tile_process(img, cond, 510, to_cpu=False))
+    rec = {'what': 'k4nerf SFTNet.tile_process (tcgen05)', 'hw': [H, W], 'ms_per_frame': ms, 'tflops': flop / ms / 1e9}
+    print(json.dumps(rec), flush=True)
+    sd_dev = {k: v.to(dev) for k, v in sd.items()}
+    for tf32 in (True, False):
+        torch.backends.cudnn.allow_tf32 = tf32
+        torch.backends.cuda.matmul.allow_tf32 = tf32
+        ms_ref, ref = timeit(lambda: sftnet.tile_process(sd_dev, img, cond, 510))
+        p = pipeline.psnr(out.cpu(), ref)
+        print(json.dumps({'what': f'torch/cuDNN same network, allow_tf32={tf32} (the reference path; includes its per-tile D2H)',
+                          'ms_per_frame': ms_ref, 'tflops': flop / ms_ref / 1e9, 'psnr_k4_vs_this': p,
+                          'out_absmax': ref.abs().max().item()}), flush=True)
+
+
+if __name__ == '__main__':
+    main()
