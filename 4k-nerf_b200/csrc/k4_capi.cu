@@ -339,7 +339,7 @@ extern "C" int k4_render_rays(const k4_scene* sc, const k4_render_args* a,
     if (sc->dev.depth > 0 && !d_viewdirs) return K4_ERR_INVALID_ARG;
     if (!d_workspace || workspace_bytes < k4_render_workspace_bytes(sc, n_rays)) return K4_ERR_WORKSPACE;
     if (!(a->stepsize > 0.f)) return K4_ERR_INVALID_ARG;
-    if (a->mlp_mode < K4_MLP_FP32 || a->mlp_mode > K4_MLP_TCGEN05) return K4_ERR_INVALID_ARG;
+    if (a->mlp_mode < K4_MLP_FP32 || a->mlp_mode > K4_MLP_TCGEN05_WS) return K4_ERR_INVALID_ARG;
     if (a->image_w > 0 && (long long)a->image_w * a->image_h != n_rays) return K4_ERR_INVALID_ARG;
     cudaStream_t s = (cudaStream_t)stream;
     const K4Dev& v = sc->dev;
@@ -374,9 +374,9 @@ extern "C" int k4_render_rays(const k4_scene* sc, const k4_render_args* a,
     rp.tile_counter = reinterpret_cast<unsigned int*>(d_workspace);
     { const char* e = getenv("K4_TC_DBG"); rp.dbg = e ? atoi(e) : 0; }
     K4_CUDA_TRY(cudaMemsetAsync(d_workspace, 0, 16, s));
-    if (a->mlp_mode == K4_MLP_TCGEN05 && v.depth > 0) {
+    if ((a->mlp_mode == K4_MLP_TCGEN05 || a->mlp_mode == K4_MLP_TCGEN05_WS) && v.depth > 0) {
         if (!k4_tc_supported(v)) return K4_ERR_UNSUPPORTED;
-        return k4_launch_march_tc(sc, rp, s);
+        return a->mlp_mode == K4_MLP_TCGEN05 ? k4_launch_march_tc(sc, rp, s) : k4_launch_march_ws(sc, rp, s);
     }
     return k4_launch_march(sc, rp, a->mlp_mode, s);
 }

@@ -103,3 +103,4 @@ void k4_set_cuda_error(cudaError_t e, const char* where);
 int k4_launch_march(const k4_scene* sc, const K4RenderParams& rp, int mlp_mode, cudaStream_t st);
 int k4_launch_march_tc(const k4_scene* sc, K4RenderParams rp, cudaStream_t st);   // K4_ERR_UNSUPPORTED if the shape has no tcgen05 build
 bool k4_tc_supported(const K4Dev& v);
+int k4_launch_march_ws(const k4_scene* sc, K4RenderParams rp, cudaStream_t st);   // warp-specialised variant (same shapes)

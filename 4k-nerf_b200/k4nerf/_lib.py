@@ -7,10 +7,10 @@ LIB_PATH = os.path.join(_HERE, 'libk4nerf.so')
 
 K4_OK = 0
 K4_KIND_DVGO, K4_KIND_DMPIGO = 0, 1
-K4_MLP_FP32, K4_MLP_F16, K4_MLP_F16X3, K4_MLP_TCGEN05 = 0, 1, 2, 3
+K4_MLP_FP32, K4_MLP_F16, K4_MLP_F16X3, K4_MLP_TCGEN05, K4_MLP_TCGEN05_WS = 0, 1, 2, 3, 4
 K4_MAX_MLP_LAYERS = 8
 MLP_MODES = {'fp32': K4_MLP_FP32, 'f16': K4_MLP_F16, 'f16x3': K4_MLP_F16X3, 'tcgen05': K4_MLP_TCGEN05,
-             'tc': K4_MLP_TCGEN05}
+             'tc': K4_MLP_TCGEN05, 'ws': K4_MLP_TCGEN05_WS}
 
 
 class SceneDesc(C.Structure):

@@ -10,7 +10,7 @@ import torch
 
 from . import _lib
 
-_DEFAULT_MLP_MODE = 'auto'     # tcgen05 kernel when the shape has a build, else mma.sync f16, else fp32
+_DEFAULT_MLP_MODE = 'auto'     # warp-specialised tcgen05 kernel when the shape has a build, else mma.sync f16, else fp32
 
 
 class SceneHandle:
@@ -142,9 +142,9 @@ class FusedRenderMixin:
         spe = int(getattr(self, 'spatial_pe', 0))
         if len(layers) == 3:
             if self._k4_kind == _lib.K4_KIND_DVGO and C == 12 and vpe == 4 and width == 128 and getattr(self, 'rgbnet_direct', True):
-                return 'tc'
+                return 'ws'
             if self._k4_kind == _lib.K4_KIND_DMPIGO and C == 9 and vpe == 0 and spe == 0 and width == 64:
-                return 'tc'
+                return 'ws'
             if width in (64, 128) and dim0 <= 64:
                 return 'f16'
         return 'fp32'

@@ -366,12 +366,13 @@ def main():
             'warmup': max(args.warmup, 3), 'ms_per_step': ms_per_step, 'higher_is_better': True,
             'scaling': 'strong', 'vs_baseline': None,
             'dtype': {'fp32': 'f32', 'f16': 'f16 operands, f32 accumulate (mma.sync)', 'f16x3': 'f16x3 split (f32-equivalent)',
-                      'tc': 'f32 geometry/interpolation/compositing; rgbnet f16 operands, f32 accumulate (tcgen05)'}[mode],
+                      'tc': 'f32 geometry/interpolation/compositing; rgbnet f16 operands, f32 accumulate (tcgen05)',
+                      'ws': 'f32 geometry/interpolation/compositing; rgbnet f16 operands, f32 accumulate (tcgen05)'}[mode],
             'data': 'synthetic', 'config': workload_config(args, world), 'mlp_mode': mode,
             'e2e': e2e, 'gpu_launches': args.steps, 'clocks': clocks,
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
                          'traffic': traffic, 'peak_source': peak_src,
-                         'kernel': 'k4_march_tc_kernel' if mode == 'tc' else 'k4_march_kernel',
+                         'kernel': {'tc': 'k4_march_tc_kernel', 'ws': 'k4_march_ws_kernel'}.get(mode, 'k4_march_kernel'),
                          'kernel_ms_per_launch': kernel_ms,
                          'algorithmic_bytes_per_ray': alg_bytes / (H * W),
                          'samples_per_ray': {'S_m': S_m / (H * W), 'S_d': S_d / (H * W), 'S_c': S_c / (H * W)},

@@ -53,7 +53,8 @@ enum { K4_KIND_DVGO = 0,                   /* DirectVoxGO,  lib/dvgo.py:23-448  
 enum { K4_MLP_FP32 = 0,                    /* fp32 FFMA, sequential accumulation (exact mode)   */
        K4_MLP_F16 = 1,                     /* tensor cores, fp16 operands, fp32 accumulate       */
        K4_MLP_F16X3 = 2,                   /* tensor cores, error-compensated 3-term fp16 split  */
-       K4_MLP_TCGEN05 = 3 };               /* tcgen05 + TMEM, fp16 operands (CTA-wide batches)   */
+       K4_MLP_TCGEN05 = 3,                 /* tcgen05 + TMEM, fp16 operands (CTA-wide batches)   */
+       K4_MLP_TCGEN05_WS = 4 };            /* same, MLP in its own warpgroup (warp-specialised)  */
 
 #define K4_MAX_MLP_LAYERS 8
 
