@@ -401,9 +401,13 @@ def time_mode(model, rays, kw, hw, mode, iters=3):
 
 
 def secondary(model, st, model_from_state, kw, dev, mode, args):
-    """configs[1] at its nominal 1008x756, and the sparse SHELL regime, same kernel and mode."""
+    """Same kernels on the other BASELINE.json configs: configs[1] at its nominal 1008x756, the sparse
+    SHELL regime at 4K, configs[2] (LLFF MPI model, lib/dmpigo) and configs[3]'s VC-Decoder."""
+    import k4nerf
     from helpers import make_state
+    from oracle import scenes, sftnet
     out = {}
+    peak, _ = hbm_peak()
     rays = frame_rays_device(HLR, WLR, POSES[0], dev)
     ms = time_mode(model, rays, kw, (HLR, WLR), mode)
     out['configs[1]_1008x756_' + args.regime] = {'rays_per_s': HLR * WLR / (ms * 1e-3), 'ms_per_frame': ms}
@@ -415,11 +419,60 @@ def secondary(model, st, model_from_state, kw, dev, mode, args):
     c = [int(x) for x in dbg['counters'].cpu().tolist()]
     ms = time_mode(m2, rays4k, kw, (H4K, W4K), mode)
     n = H4K * W4K
-    peak, _ = hbm_peak()
     b = algorithmic_bytes(n, c[0], c[1], c[2])
     out['4032x3024_' + other] = {'rays_per_s': n / (ms * 1e-3), 'ms_per_frame': ms,
                                  'algorithmic_bytes_per_ray': b / n, 'roofline_frac': b / (ms * 1e-3) / 1e9 / peak,
                                  'samples_per_ray': {'S_m': c[0] / n, 'S_d': c[1] / n, 'S_c': c[2] / n}}
+    del m2, st2, rays4k, dbg
+    torch.cuda.empty_cache()
+    # configs[2]: LLFF MPI model [384,384,256], k0 9 ch, rgbnet 15-64-64-3, 256 samples/ray, NDC rays
+    try:
+        st3 = make_state('cfgB', xy=384, depth=256, regime='shell')
+        m3 = model_from_state(st3, dev)
+        kw3 = dict(scenes.RENDER_KW_MPI)
+        mode3 = m3.resolve_mlp_mode('auto')
+        for (H, W) in ((HLR, WLR), (H4K, W4K)):
+            K, c2w = scenes.llff_camera(H, W, (0.05, -0.03, 0.0))
+            ro, rd, vd = k4nerf.get_rays_of_a_view(H, W, K, c2w.to(dev), True, False, False, False)
+            r3 = (ro.view(-1, 3), rd.view(-1, 3), vd.view(-1, 3))
+            dbg = m3.render_rays(*r3, kw3, image_hw=(H, W), mlp_mode=mode3, debug=True)
+            c = [int(x) for x in dbg['counters'].cpu().tolist()]
+            ms = time_mode(m3, r3, kw3, (H, W), mode3, iters=2)
+            n = H * W
+            b = 68 * n + c[0] + 40 * c[1] + 32 * 9 * c[2]
+            out[f'configs[2]_llff_mpi_{W}x{H}_shell'] = {
+                'rays_per_s': n / (ms * 1e-3), 'ms_per_frame': ms, 'mlp_mode': mode3,
+                'algorithmic_bytes_per_ray': b / n, 'roofline_frac': b / (ms * 1e-3) / 1e9 / peak,
+                'samples_per_ray': {'S_m': c[0] / n, 'S_d': c[1] / n, 'S_c': c[2] / n}}
+            del ro, rd, vd, r3, dbg
+        del m3, st3
+        torch.cuda.empty_cache()
+    except Exception as e:           # never lose the headline line to a secondary measurement
+        out['configs[2]_error'] = repr(e)
+    # configs[3]: VC-Decoder, 1008x756 -> 4032x3024, tile 510 / pad 10 (run_sr.py --test_tile 510)
+    try:
+        net = k4nerf.SFTNet(3, 4, 64, 5, 32, 1)
+        net.load_state_dict(sftnet.random_state_dict(seed=3, scale=1.0))
+        net = net.to(dev)
+        g = torch.Generator().manual_seed(1)
+        img = torch.rand(1, 3, HLR, WLR, generator=g).to(dev)
+        cond = torch.rand(1, HLR, WLR, generator=g).to(dev)
+        net.tile_process(img, cond, 510, to_cpu=False)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3):
+            net.tile_process(img, cond, 510, to_cpu=False)
+        e1.record()
+        torch.cuda.synchronize()
+        ms_sr = e0.elapsed_time(e1) / 3
+        flop = 2 * 5188864 * sum((p[1] - p[0]) * (p[3] - p[2]) for p in sftnet.tile_plan(HLR, WLR, 510, 10))
+        lr = out['configs[1]_1008x756_' + args.regime]['ms_per_frame']
+        out['configs[3]_vc_decoder_1008x756_to_4032x3024'] = {
+            'ms_per_frame': ms_sr, 'tflops': flop / ms_sr / 1e9, 'algorithmic_tflop_per_frame': flop / 1e12,
+            'full_4k_nerf_frame_ms (march 1008x756 ' + args.regime + ' + decode)': lr + ms_sr}
+    except Exception as e:
+        out['configs[3]_error'] = repr(e)
     return out
 
 
