@@ -23,6 +23,7 @@
 // residual trunk and all SFT / CondNet math stay fp32.  (The reference itself runs these convs with
 // TF32 operands: torch.backends.cudnn.allow_tf32 defaults to True.)
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -298,6 +299,211 @@ __global__ void __launch_bounds__(128) sft_kernel(const __grid_constant__ SftPar
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// SFT layer on the tensor cores: both 1x1-conv branches are two chained K=32 GEMMs per 128-pixel
+// tile -- L0: [cond] x [scale_conv0 ; shift_conv0] (N = 64), LeakyReLU + fp16 repack in TMEM,
+// L1: scale = H[:, :32] x scale_conv1, shift = H[:, 32:] x shift_conv1 (A straight from TMEM) --
+// and the modulation y = x*(scale+1)+shift is the epilogue (the +1 lives in the bias tile).
+// Persistent CTAs: the layer's 16-22 KB operand blob is staged once per CTA.
+// ---------------------------------------------------------------------------------------------
+struct SftBlob { int off_b0, off_b1s, off_b1h, off_bias0, off_bias1s, off_bias1h, off_ones, total; };
+__host__ __device__ inline SftBlob sft_blob_layout(int cout) {
+    SftBlob L; int o = 0;
+    L.off_b0 = o; o += 64 * 64;
+    L.off_b1s = o; o += cout * 64;
+    L.off_b1h = o; o += cout * 64;
+    L.off_bias0 = o; o += 64 * 32;
+    L.off_bias1s = o; o += cout * 32;
+    L.off_bias1h = o; o += cout * 32;
+    L.off_ones = o; o += 128 * 32;
+    L.total = o;
+    return L;
+}
+
+__device__ __forceinline__ void sr_mma_ts(uint32_t d, uint32_t a_tmem, uint64_t b, uint32_t idesc, uint32_t acc) {
+    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n}\n"
+                 :: "r"(d), "r"(a_tmem), "l"(b), "r"(idesc), "r"(acc), "r"(0u) : "memory");
+}
+__device__ __forceinline__ void sr_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                 "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];\n"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                   "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                   "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                 : "r"(taddr));
+}
+__device__ __forceinline__ void sr_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+                 "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};\n"
+                 :: "r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+                    "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]) : "memory");
+}
+
+struct SftTcParams {
+    const float* cond;               // [P,32] fp32
+    const unsigned char* blob;       // sft_blob_layout(COUT)
+    const float* x_f; const __half* x_h; int xh_cstride, xh_c0;
+    __half* dst_h; int dst_cstride, dst_c0;
+    float* dst_f; const float* res_f; float res_scale;
+    long long P; int n_tiles;
+};
+
+template <int COUT>
+__global__ void __launch_bounds__(128) sft_tc_kernel(const __grid_constant__ SftTcParams p) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    const SftBlob BL = sft_blob_layout(COUT);
+    unsigned char* blob = smem;
+    unsigned char* atile = smem + ((BL.total + 1023) & ~1023);          // [128][32] fp16 canonical, 8 KB
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(atile + 8192);
+    uint32_t* tslot = reinterpret_cast<uint32_t*>(atile + 8192 + 16);
+    constexpr int TCOLS = (COUT == 64) ? 256 : 128;
+    constexpr uint32_t D0 = 0, D1S = 64, D1H = 64 + COUT;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int i = tid; i < BL.total / 16; i += 128) cp_async16(blob + i * 16, p.blob + i * 16, 16);
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+    if (tid == 0) {
+        sr_mbar_init(mbar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" :: "r"(sr_s32(tslot)), "r"((uint32_t)TCOLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+    }
+    asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    const uint32_t tbase = *tslot;
+    const uint32_t tl = tbase + ((uint32_t)(warp * 32) << 16);
+    const uint32_t blob_s = sr_s32(blob), a_s = sr_s32(atile);
+    uint32_t ph = 0;
+
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        const long long pix = (long long)tile * 128 + tid;
+        const bool valid = pix < p.P;
+        {   // cond row -> fp16, canonical layout (row = tid, 4 chunks of 8 channels)
+            const float4* cp = reinterpret_cast<const float4*>(p.cond + (valid ? pix : 0) * 32);
+#pragma unroll
+            for (int kc = 0; kc < 4; ++kc) {
+                const float4 a = __ldg(cp + 2 * kc), b = __ldg(cp + 2 * kc + 1);
+                __half2 h[4] = {__floats2half2_rn(a.x, a.y), __floats2half2_rn(a.z, a.w), __floats2half2_rn(b.x, b.y), __floats2half2_rn(b.z, b.w)};
+                *reinterpret_cast<uint4*>(atile + tc_canon_off(tid, kc, 4)) = *reinterpret_cast<uint4*>(h);
+            }
+        }
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+        __syncthreads();
+        if (tid == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+            const uint32_t id64 = sr_idesc(128, 64);
+            sr_mma_ss(tbase + D0, sr_desc(a_s, 128, 512), sr_desc(blob_s + BL.off_b0, 128, 512), id64, 0);
+            sr_mma_ss(tbase + D0, sr_desc(a_s + 256, 128, 512), sr_desc(blob_s + BL.off_b0 + 256, 128, 512), id64, 1);
+            sr_mma_ss(tbase + D0, sr_desc(blob_s + BL.off_ones, 128, 256), sr_desc(blob_s + BL.off_bias0, 128, 256), id64, 1);
+            sr_commit(mbar);
+        }
+        sr_mbar_wait(mbar, ph); ph ^= 1;
+        asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {   // LeakyReLU(0.2) + fp16 repack: H_scale -> cols [0,16), H_shift -> cols [16,32)
+            uint32_t v[32], h[16];
+            sr_ld32(tl + D0 + c * 32, v);
+            asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const float a = __uint_as_float(v[2 * j]), b = __uint_as_float(v[2 * j + 1]);
+                const __half2 hh = __floats2half2_rn(fmaxf(a, 0.2f * a), fmaxf(b, 0.2f * b));
+                h[j] = *reinterpret_cast<const uint32_t*>(&hh);
+            }
+            sr_st16(tl + D0 + c * 16, h);
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+        __syncthreads();
+        if (tid == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+            const uint32_t idc = sr_idesc(128, COUT);
+            sr_mma_ts(tbase + D1S, tbase + D0 + 0, sr_desc(blob_s + BL.off_b1s, 128, 512), idc, 0);
+            sr_mma_ts(tbase + D1S, tbase + D0 + 8, sr_desc(blob_s + BL.off_b1s + 256, 128, 512), idc, 1);
+            sr_mma_ss(tbase + D1S, sr_desc(blob_s + BL.off_ones, 128, 256), sr_desc(blob_s + BL.off_bias1s, 128, 256), idc, 1);
+            sr_mma_ts(tbase + D1H, tbase + D0 + 16, sr_desc(blob_s + BL.off_b1h, 128, 512), idc, 0);
+            sr_mma_ts(tbase + D1H, tbase + D0 + 24, sr_desc(blob_s + BL.off_b1h + 256, 128, 512), idc, 1);
+            sr_mma_ss(tbase + D1H, sr_desc(blob_s + BL.off_ones, 128, 256), sr_desc(blob_s + BL.off_bias1h, 128, 256), idc, 1);
+            sr_commit(mbar);
+        }
+        sr_mbar_wait(mbar, ph); ph ^= 1;
+        asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+#pragma unroll
+        for (int c16 = 0; c16 < COUT / 16; ++c16) {
+            uint32_t sv[16], hv[16];
+            sr_ld16(tl + D1S + c16 * 16, sv);
+            sr_ld16(tl + D1H + c16 * 16, hv);
+            asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+            if (!valid) continue;
+            float x[16];
+            if (p.x_f) {
+                const float4* xp = reinterpret_cast<const float4*>(p.x_f + pix * 64 + c16 * 16);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) { const float4 t = __ldg(xp + q); x[4 * q] = t.x; x[4 * q + 1] = t.y; x[4 * q + 2] = t.z; x[4 * q + 3] = t.w; }
+            } else {
+                const uint4* xp = reinterpret_cast<const uint4*>(p.x_h + pix * p.xh_cstride + p.xh_c0 + c16 * 16);
+                const uint4 u0 = xp[0], u1 = xp[1];
+                const __half2* hp0 = reinterpret_cast<const __half2*>(&u0);
+                const __half2* hp1 = reinterpret_cast<const __half2*>(&u1);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) { const float2 a = __half22float2(hp0[q]), b = __half22float2(hp1[q]); x[2 * q] = a.x; x[2 * q + 1] = a.y; x[8 + 2 * q] = b.x; x[8 + 2 * q + 1] = b.y; }
+            }
+            float y[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) y[j] = fmaf(x[j], __uint_as_float(sv[j]), __uint_as_float(hv[j]));   // scale tile already holds scale+1
+            if (p.dst_f) {
+                const float4* rp = reinterpret_cast<const float4*>(p.res_f + pix * 64 + c16 * 16);
+                float4* dp = reinterpret_cast<float4*>(p.dst_f + pix * 64 + c16 * 16);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float4 r = __ldg(rp + q);
+                    dp[q] = make_float4(y[4 * q] * p.res_scale + r.x, y[4 * q + 1] * p.res_scale + r.y, y[4 * q + 2] * p.res_scale + r.z, y[4 * q + 3] * p.res_scale + r.w);
+                }
+            } else {
+                __half2 h[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) h[j] = __floats2half2_rn(y[2 * j], y[2 * j + 1]);
+                uint4* d = reinterpret_cast<uint4*>(p.dst_h + pix * p.dst_cstride + p.dst_c0 + c16 * 16);
+                d[0] = *reinterpret_cast<uint4*>(&h[0]);
+                d[1] = *reinterpret_cast<uint4*>(&h[4]);
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+        __syncthreads();       // D1S/D1H and the A tile are free again
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" :: "r"(tbase), "r"((uint32_t)TCOLS) : "memory");
+}
+
+// fp32 SFT weights (sft_kernel packing order s0,s0b,h0,h0b,s1,s1b,h1,h1b) -> tcgen05 operand blob
+__global__ void pack_sft_blob_kernel(const float* __restrict__ w, unsigned char* __restrict__ blob, int cout) {
+    const SftBlob BL = sft_blob_layout(cout);
+    const float* s0 = w; const float* s0b = s0 + 1024; const float* h0 = s0b + 32; const float* h0b = h0 + 1024;
+    const float* s1 = h0b + 32; const float* s1b = s1 + cout * 32; const float* h1 = s1b + cout; const float* h1b = h1 + cout * 32;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    auto put = [&](int off, int row, int k, int kch, float v) {
+        *reinterpret_cast<__half*>(blob + off + tc_canon_off(row, k >> 3, kch) + (k & 7) * 2) = __float2half_rn(v);
+    };
+    auto put_bias = [&](int off, int row, float b) {
+        const __half hi = __float2half_rn(b);
+        put(off, row, 0, 2, __half2float(hi));
+        put(off, row, 1, 2, b - __half2float(hi));
+    };
+    if (i < 64 * 32) { const int n = i >> 5, k = i & 31; put(BL.off_b0, n, k, 4, n < 32 ? s0[n * 32 + k] : h0[(n - 32) * 32 + k]); }
+    if (i < cout * 32) { const int n = i >> 5, k = i & 31; put(BL.off_b1s, n, k, 4, s1[n * 32 + k]); put(BL.off_b1h, n, k, 4, h1[n * 32 + k]); }
+    if (i < 64) put_bias(BL.off_bias0, i, i < 32 ? s0b[i] : h0b[i - 32]);
+    if (i < cout) { put_bias(BL.off_bias1s, i, s1b[i] + 1.f); put_bias(BL.off_bias1h, i, h1b[i]); }
+    if (i < 128) { put(BL.off_ones, i, 0, 2, 1.f); put(BL.off_ones, i, 1, 2, 1.f); }
+}
+
 // CondNet: conv3x3(1->64) lrelu, 1x1 64->64 lrelu, 1x1 64->64 lrelu, 1x1 64->32   (lib/sr_esrnet.py:440-444)
 struct CondParams { const float* cond_in; const float* w; float* cond_out; int H, W; };   // w: c0 [64][9], b0[64], c2 [64][64], b2, c4 [64][64], b4, c6 [32][64], b6
 
@@ -382,7 +588,7 @@ __global__ void pack_conv3x3_kernel(const float* __restrict__ W, unsigned char* 
 // host side
 // ------------------------------------------------------------------------------------------------
 struct SrConv { unsigned char* wpack; float* bias; int cin_pad, cout, npad; };
-struct SrSft { float* w; int cout; };
+struct SrSft { float* w; unsigned char* blob; int cout; };
 
 struct k4_srnet {
     int num_feat, num_block, num_grow, num_cond, n_in, scale;
@@ -438,6 +644,12 @@ int make_sft(k4_srnet* n, SrSft& f, const float* const* pw, int cout, cudaStream
     cp(pw[2], (size_t)cout * 32); cp(pw[3], cout);  // scale_conv1 w, b
     cp(pw[6], (size_t)cout * 32); cp(pw[7], cout);  // shift_conv1 w, b
     K4_CUDA_TRY(cudaGetLastError());
+    const SftBlob BL = sft_blob_layout(cout);
+    st = sr_alloc(n, (void**)&f.blob, (size_t)BL.total);
+    if (st) return st;
+    K4_CUDA_TRY(cudaMemsetAsync(f.blob, 0, BL.total, s));
+    pack_sft_blob_kernel<<<8, 256, 0, s>>>(f.w, f.blob, cout);
+    K4_CUDA_TRY(cudaGetLastError());
     return K4_OK;
 }
 
@@ -472,9 +684,39 @@ int launch_sft(const SftParams& p, cudaStream_t s) {
     return K4_OK;
 }
 
+template <int COUT>
+int launch_sft_tc(const SftTcParams& p, cudaStream_t s) {
+    const SftBlob BL = sft_blob_layout(COUT);
+    constexpr int per_sm_c = (COUT == 64) ? 2 : 4;       // TMEM: 256 / 128 columns per CTA
+    // ask for enough shared memory that no more than `per_sm` CTAs can share an SM: a CTA beyond the
+    // TMEM budget would otherwise sit in tcgen05.alloc until a neighbour exits
+    int smem = ((BL.total + 1023) & ~1023) + 8192 + 64;
+    if (smem < (200 * 1024) / per_sm_c) smem = (200 * 1024) / per_sm_c;
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        K4_CUDA_TRY(cudaGetDevice(&dev));
+        K4_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        K4_CUDA_TRY(cudaFuncSetAttribute(sft_tc_kernel<COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    }
+    const int per_sm = per_sm_c;
+    int grid = p.n_tiles < sms * per_sm ? p.n_tiles : sms * per_sm;
+    sft_tc_kernel<COUT><<<grid, 128, smem, s>>>(p);
+    K4_CUDA_TRY(cudaGetLastError());
+    return K4_OK;
+}
+
 int run_sft(const SrSft& f, SftParams p, cudaStream_t s) {
-    p.w = f.w;
-    return f.cout == 64 ? launch_sft<64>(p, s) : launch_sft<32>(p, s);
+    static const bool use_fp32 = getenv("K4_SFT_FP32") != nullptr;      // development switch: fp32 FFMA kernel
+    if (use_fp32) {
+        p.w = f.w;
+        return f.cout == 64 ? launch_sft<64>(p, s) : launch_sft<32>(p, s);
+    }
+    SftTcParams q{};
+    q.cond = p.cond; q.blob = f.blob; q.x_f = p.x_f; q.x_h = p.x_h; q.xh_cstride = p.xh_cstride; q.xh_c0 = p.xh_c0;
+    q.dst_h = p.dst_h; q.dst_cstride = p.dst_cstride; q.dst_c0 = p.dst_c0; q.dst_f = p.dst_f; q.res_f = p.res_f;
+    q.res_scale = p.res_scale; q.P = p.P; q.n_tiles = (int)((p.P + 127) / 128);
+    return f.cout == 64 ? launch_sft_tc<64>(q, s) : launch_sft_tc<32>(q, s);
 }
 
 }  // namespace

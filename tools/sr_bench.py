@@ -40,14 +40,18 @@ def main():
     rec = {'what': 'k4nerf SFTNet.tile_process (tcgen05)', 'hw': [H, W], 'ms_per_frame': ms, 'tflops': flop / ms / 1e9}
     print(json.dumps(rec), flush=True)
     sd_dev = {k: v.to(dev) for k, v in sd.items()}
+    refs = {}
     for tf32 in (True, False):
         torch.backends.cudnn.allow_tf32 = tf32
         torch.backends.cuda.matmul.allow_tf32 = tf32
         ms_ref, ref = timeit(lambda: sftnet.tile_process(sd_dev, img, cond, 510))
+        refs[tf32] = ref
         p = pipeline.psnr(out.cpu(), ref)
         print(json.dumps({'what': f'torch/cuDNN same network, allow_tf32={tf32} (the reference path; includes its per-tile D2H)',
                           'ms_per_frame': ms_ref, 'tflops': flop / ms_ref / 1e9, 'psnr_k4_vs_this': p,
                           'out_absmax': ref.abs().max().item()}), flush=True)
+    print(json.dumps({'what': 'cuDNN TF32 (reference default) vs cuDNN fp32: the arithmetic noise of the reference itself',
+                      'psnr': pipeline.psnr(refs[True], refs[False])}), flush=True)
 
 
 if __name__ == '__main__':
