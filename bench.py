@@ -209,7 +209,8 @@ def workload_config(args, n_gpus):
         'workload': 'north-star target: BASELINE configs[1] model (DirectVoxGO 160^3, k0 12 ch, rgbnet 39-128-128-3, '
                     'stepsize 0.5) marched at 4032x3024 rays/step',
         'regime': args.regime, 'rays_per_step': H4K * W4K, 'grid': [GRID_RES] * 3, 'k0_dim': 12,
-        'mlp': [39, 128, 128, 3], 'parallelism': f'row-bands x{n_gpus}' + (' + nccl all_gather' if n_gpus > 1 else ''),
+        'mlp': [39, 128, 128, 3],
+        'parallelism': f'8-row blocks dealt round-robin over {n_gpus} rank(s)' + (' + nccl all_gather' if n_gpus > 1 else ''),
         'l2_policy': 'inputs larger than L2 (439 MB rays + 213 MB grids per step), pose changes every step',
     }
 
@@ -235,6 +236,7 @@ def main():
     dev = torch.device('cuda', local_rank)
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')      # keep stdout = the one JSON line
         dist.init_process_group('nccl', device_id=dev)
 
     st, model_from_state = build_scene(args.regime)
@@ -242,18 +244,21 @@ def main():
     mode = model.resolve_mlp_mode(args.mlp_mode or model.mlp_mode)
     kw = dict(near=2.0, far=6.0, bg=1, stepsize=0.5, inverse_y=False, flip_x=False, flip_y=False, render_depth=True)
 
-    # inputs resident in HBM before the timed region: one ray set per pose, this rank's band only
+    # inputs resident in HBM before the timed region: one ray set per pose, this rank's rows only
+    # (8-row blocks dealt round-robin over the ranks: every rank gets the same mix of long and short rays)
     H, W = H4K, W4K
-    r0, r1 = kdist.band_range(H, rank, world)
+    rows = kdist.cyclic_rows(H, rank, world).to(dev) if world > 1 else torch.arange(H, device=dev)
+    n_rows = int(rows.numel())
+    r0, r1 = 0, n_rows                                   # local image = this rank's rows, in order
     bands = []
     for pose in POSES:
         ro, rd, vd = frame_rays_device(H, W, pose, dev)
-        sl = slice(r0 * W, r1 * W)
-        bands.append((ro[sl].clone(), rd[sl].clone(), vd[sl].clone()))
+        sel = (lambda t: t.view(H, W, 3)[rows].reshape(-1, 3).contiguous()) if world > 1 else (lambda t: t)
+        bands.append((sel(ro), sel(rd), sel(vd)))
         del ro, rd, vd
     torch.cuda.empty_cache()
-    n_band = (r1 - r0) * W
-    n_pad = kdist.band_rows(H, world) * W
+    n_band = n_rows * W
+    n_pad = (kdist.cyclic_pad_rows(H, world) if world > 1 else H) * W
     gathered = torch.empty(world * 5 * n_pad, device=dev, dtype=torch.float32) if world > 1 else None
 
     def step(i):

@@ -34,15 +34,17 @@ def _worker(rank, world, port, H, W, q):
     dist.init_process_group('gloo', rank=rank, world_size=world)
     g = torch.Generator().manual_seed(5)
     ro, rd, vd = (torch.randn(H * W, 3, generator=g) for _ in range(3))
-    full = kdist.render_frame_sharded(_fake_render, ro, rd, vd, H, W)
     ref = _fake_render(ro, rd, vd, (H, W))
-    ok = all(torch.equal(full[k], ref[k]) for k in ('rgb_marched', 'depth', 'alphainv_last'))
+    ok = True
+    for layout in ('cyclic', 'bands'):
+        full = kdist.render_frame_sharded(_fake_render, ro, rd, vd, H, W, layout=layout)
+        ok = ok and all(torch.equal(full[k], ref[k]) for k in ('rgb_marched', 'depth', 'alphainv_last'))
     r0, r1 = kdist.band_range(H, rank, world)
     q.put((rank, ok, r0, r1))
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize('H,W', [(8, 6), (7, 5), (1, 9)])
+@pytest.mark.parametrize('H,W', [(8, 6), (7, 5), (1, 9), (37, 4)])
 def test_row_band_sharding_world2_gloo(H, W):
     ctx = mp.get_context('spawn')
     q = ctx.Queue()
@@ -69,3 +71,6 @@ def test_band_arithmetic():
                 assert 0 <= r0 <= r1 <= H and r1 - r0 <= kdist.band_rows(H, world)
                 cover += list(range(r0, r1))
             assert cover == list(range(H))
+            cyc = sorted(int(x) for r in range(world) for x in kdist.cyclic_rows(H, r, world))
+            assert cyc == list(range(H))
+            assert all(kdist.cyclic_rows(H, r, world).numel() <= kdist.cyclic_pad_rows(H, world) for r in range(world))
