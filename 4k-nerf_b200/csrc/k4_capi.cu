@@ -372,7 +372,6 @@ extern "C" int k4_render_rays(const k4_scene* sc, const k4_render_args* a,
     rp.alphainv = out->d_alphainv_last;
     rp.ray_stats = out->d_ray_stats; rp.t_minmax = out->d_t_minmax; rp.counters = out->d_counters;
     rp.tile_counter = reinterpret_cast<unsigned int*>(d_workspace);
-    { const char* e = getenv("K4_TC_DBG"); rp.dbg = e ? atoi(e) : 0; }
     K4_CUDA_TRY(cudaMemsetAsync(d_workspace, 0, 16, s));
     if ((a->mlp_mode == K4_MLP_TCGEN05 || a->mlp_mode == K4_MLP_TCGEN05_WS) && v.depth > 0) {
         if (!k4_tc_supported(v)) return K4_ERR_UNSUPPORTED;

@@ -88,7 +88,6 @@ struct K4RenderParams {
     float* t_minmax;
     unsigned long long* counters;
     unsigned int* tile_counter;
-    int dbg;                      // K4_TC_DBG env (development only): bit0 = warpgroup 1 idle, bit1 = one tile per warpgroup
 };
 
 // error plumbing (k4_capi.cu)

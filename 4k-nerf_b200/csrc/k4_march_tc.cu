@@ -284,8 +284,6 @@ k4_march_tc_kernel(const __grid_constant__ K4Dev s, const __grid_constant__ K4Re
         wg_bar(wg);
         const long long tile = tile_slot[iter & 1];
         if (tile >= rp.n_tiles) break;
-        if ((rp.dbg & 1) && wg == 1) break;
-        if ((rp.dbg & 2) && iter > 0) break;
 
         long long ray_i;
         if (rp.image_w > 0) {

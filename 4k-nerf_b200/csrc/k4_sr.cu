@@ -4,8 +4,9 @@
 // launches per tile with
 //
 //   conv3x3_tc_kernel<N>   every 3x3 convolution as an im2col-free implicit GEMM on tcgen05:
-//       a CTA owns a 16x8 pixel tile (M = 128 rows = y*8+x); per 32-channel slice of the input the
-//       (16+2)x(8+2) halo is staged ONCE in shared memory as four 8-channel planes
+//       a CTA owns four side-by-side 16x8 pixel tiles (M = 128 rows = y*8+x each) that share every
+//       weight stage; per 32-channel slice of the input the (16+2)x(32+2) halo is staged ONCE in
+//       shared memory as four 8-channel planes
 //       [plane][hy][hx] x 16 B -- which IS the canonical K-major UMMA layout (core matrix = 8
 //       horizontally adjacent pixels, SBO = halo row pitch, LBO = plane pitch) -- so the nine taps
 //       are nine shared-memory descriptors that differ only in their start address
@@ -67,12 +68,14 @@ __device__ __forceinline__ void cp_async16(void* dst_smem, const void* src, int 
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" :: "r"(sr_s32(dst_smem)), "l"(src), "r"(src_bytes) : "memory");
 }
 
-constexpr int SR_TY = 16, SR_TX = 8;                 // output tile (pixels)
+constexpr int SR_TM = 4;                             // M tiles (16x8 pixels each) per CTA, side by side in x:
+                                                     // they share one weight stage (4x less L2->smem weight traffic)
+constexpr int SR_TY = 16, SR_TX = 8 * SR_TM;         // output region of a CTA (pixels)
 constexpr int SR_HY = SR_TY + 2, SR_HX = SR_TX + 2;  // halo
-constexpr int SR_ROW = SR_HX * 16;                   // 160 B: one halo row of one 8-channel plane
-constexpr int SR_PLANE = SR_HY * SR_ROW;             // 2880 B
+constexpr int SR_ROW = SR_HX * 16;                   // 544 B: one halo row of one 8-channel plane
+constexpr int SR_PLANE = SR_HY * SR_ROW;             // 9792 B
 constexpr int SR_CK = 32;                            // input channels per K slice
-constexpr int SR_A_STAGE = (SR_CK / 8) * SR_PLANE;   // 11520 B
+constexpr int SR_A_STAGE = (SR_CK / 8) * SR_PLANE;   // 39168 B
 
 enum { SRM_STORE_F16 = 0,      // dst_h[c0..c0+N) = act(acc + b)
        SRM_TRUNK = 1,          // dst_f = (acc + b) * scale + add_f                  (conv5: x5*0.2 + x)
@@ -96,7 +99,8 @@ __global__ void __launch_bounds__(128) conv3x3_tc_kernel(const __grid_constant__
     constexpr int B_TAP = N * SR_CK * 2;               // bytes of one tap's [N][32] tile
     constexpr int B_STAGE = 9 * B_TAP;
     constexpr int STAGE = SR_A_STAGE + B_STAGE;
-    constexpr int TCOLS = (N < 32) ? 32 : N;
+    constexpr int NACC = (N < 16) ? 16 : N;              // accumulator columns per M tile
+    constexpr int TCOLS = (SR_TM * NACC < 32) ? 32 : SR_TM * NACC;
     extern __shared__ __align__(1024) unsigned char smem[];
     uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + 2 * STAGE);      // [2] MMA-done per stage
     uint32_t* tslot = reinterpret_cast<uint32_t*>(smem + 2 * STAGE + 16);
@@ -157,15 +161,18 @@ __global__ void __launch_bounds__(128) conv3x3_tc_kernel(const __grid_constant__
         if (tid == 0) {
             asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
             const uint32_t a0 = sr_s32(smem + st * STAGE), b0 = a0 + SR_A_STAGE;
-            const uint32_t idesc = sr_idesc(128, N < 16 ? 16 : N);
+            const uint32_t idesc = sr_idesc(128, NACC);
+#pragma unroll 1
+            for (int m = 0; m < SR_TM; ++m) {
 #pragma unroll
-            for (int t = 0; t < 9; ++t) {
-                const int dy = t / 3, dx = t - dy * 3;
+                for (int t = 0; t < 9; ++t) {
+                    const int dy = t / 3, dx = t - dy * 3;
 #pragma unroll
-                for (int s = 0; s < SR_CK / 16; ++s) {
-                    const uint64_t ad = sr_desc(a0 + (2 * s) * SR_PLANE + dy * SR_ROW + dx * 16, SR_PLANE, SR_ROW);
-                    const uint64_t bd = sr_desc(b0 + t * B_TAP + s * 256, 128, (SR_CK / 8) * 128);
-                    sr_mma_ss(tbase, ad, bd, idesc, (c | t | s) != 0);
+                    for (int s = 0; s < SR_CK / 16; ++s) {
+                        const uint64_t ad = sr_desc(a0 + (2 * s) * SR_PLANE + dy * SR_ROW + (m * 8 + dx) * 16, SR_PLANE, SR_ROW);
+                        const uint64_t bd = sr_desc(b0 + t * B_TAP + s * 256, 128, (SR_CK / 8) * 128);
+                        sr_mma_ss(tbase + m * NACC, ad, bd, idesc, (c | t | s) != 0);
+                    }
                 }
             }
             sr_commit(mbar + st);
@@ -178,14 +185,16 @@ __global__ void __launch_bounds__(128) conv3x3_tc_kernel(const __grid_constant__
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
 
     // ---------------- epilogue: thread r = y*8 + x owns one output pixel ----------------
-    const int py = y0 + (tid >> 3), px = x0 + (tid & 7);
+    const uint32_t tl = tbase + ((uint32_t)(warp * 32) << 16);
+#pragma unroll 1
+    for (int m = 0; m < SR_TM; ++m) {
+    const int py = y0 + (tid >> 3), px = x0 + m * 8 + (tid & 7);
     const bool inside = (py < p.H) & (px < p.W);
     const size_t pix = (size_t)py * p.W + px;
-    const uint32_t tl = tbase + ((uint32_t)(warp * 32) << 16);
 #pragma unroll
-    for (int c16 = 0; c16 < (N < 16 ? 16 : N) / 16; ++c16) {
+    for (int c16 = 0; c16 < NACC / 16; ++c16) {
         uint32_t v[16];
-        sr_ld16(tl + c16 * 16, v);
+        sr_ld16(tl + m * NACC + c16 * 16, v);
         asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
         if (!inside) continue;
         float o[16];
@@ -231,6 +240,7 @@ __global__ void __launch_bounds__(128) conv3x3_tc_kernel(const __grid_constant__
             for (int j = 0; j < 16; ++j)
                 if (c16 * 16 + j < p.n_valid) p.out_nchw[(size_t)(c16 * 16 + j) * p.H * p.W + pix] = o[j];
         }
+    }
     }
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
     __syncthreads();
