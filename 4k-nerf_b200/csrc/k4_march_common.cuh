@@ -72,26 +72,25 @@ __device__ __forceinline__ void corner_weights(const Cell& c, float w[8]) {
 }
 
 // Corner k of ATen's order: dz = k&1 (world z), dy = (k>>1)&1, dx = (k>>2)&1.
-// ATen skips out-of-range corners (zero padding).  Only in-box points reach this function, and for
-// those grid_sampler's coordinate g lies in [0, size-1] (p >= xyz_min => g >= 0; p <= xyz_max and
-// len = xyz_max - xyz_min computed by the same subtraction => g <= size-1), so the low corner is always
-// valid and the high corner is out of range only when g == size-1 exactly, where its weight is
-// exactly 0.  Zeroing that axis factor (=> every product containing it is exactly 0) and re-using
-// the low index is therefore identical to skipping the corner, for finite grids.
+// Out-of-range corners are skipped by ATen (zero padding); in-box points only ever have the +1
+// corner out of range, with weight exactly 0, so clamping the index and zeroing the weight is
+// identical for finite grids.
 __device__ __forceinline__ void corner_setup(const K4Dev& s, const Cell& c, float w[8], int idx[8]) {
-    const bool vx1 = (c.x0 + 1) < s.X, vy1 = (c.y0 + 1) < s.Y, vz1 = (c.z0 + 1) < s.Z;
-    Cell cc = c;
-    if (!vx1) cc.wx1 = 0.f;
-    if (!vy1) cc.wy1 = 0.f;
-    if (!vz1) cc.wz1 = 0.f;
-    corner_weights(cc, w);
-    const int x0 = min(max(c.x0, 0), s.X - 1), y0 = min(max(c.y0, 0), s.Y - 1), z0 = min(max(c.z0, 0), s.Z - 1);
-    const int base = (x0 * s.Y + y0) * s.Z + z0;
-    const int dz = vz1 ? 1 : 0, dy = vy1 ? s.Z : 0, dx = vx1 ? s.Y * s.Z : 0;
-    idx[0] = base;           idx[1] = base + dz;
-    idx[2] = base + dy;      idx[3] = base + dy + dz;
-    idx[4] = base + dx;      idx[5] = base + dx + dz;
-    idx[6] = base + dx + dy; idx[7] = base + dx + dy + dz;
+    corner_weights(c, w);
+    int x1 = c.x0 + 1, y1 = c.y0 + 1, z1 = c.z0 + 1;
+    bool vx0 = (c.x0 >= 0) & (c.x0 < s.X), vx1 = (x1 >= 0) & (x1 < s.X);
+    bool vy0 = (c.y0 >= 0) & (c.y0 < s.Y), vy1 = (y1 >= 0) & (y1 < s.Y);
+    bool vz0 = (c.z0 >= 0) & (c.z0 < s.Z), vz1 = (z1 >= 0) & (z1 < s.Z);
+    int cx0 = min(max(c.x0, 0), s.X - 1), cx1 = min(max(x1, 0), s.X - 1);
+    int cy0 = min(max(c.y0, 0), s.Y - 1), cy1 = min(max(y1, 0), s.Y - 1);
+    int cz0 = min(max(c.z0, 0), s.Z - 1), cz1 = min(max(z1, 0), s.Z - 1);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        bool v = ((k & 1) ? vz1 : vz0) & ((k & 2) ? vy1 : vy0) & ((k & 4) ? vx1 : vx0);
+        int xx = (k & 4) ? cx1 : cx0, yy = (k & 2) ? cy1 : cy0, zz = (k & 1) ? cz1 : cz0;
+        idx[k] = (xx * s.Y + yy) * s.Z + zz;
+        if (!v) w[k] = 0.f;
+    }
 }
 
 __device__ __forceinline__ float interp_density(const K4Dev& s, const float w[8], const int idx[8]) {

@@ -4,13 +4,13 @@
 // launches per tile with
 //
 //   conv3x3_tc_kernel<N>   every 3x3 convolution as an im2col-free implicit GEMM on tcgen05:
-//       a CTA owns four side-by-side 16x8 pixel tiles (M = 128 rows = y*8+x each) that share every
-//       weight stage; per 32-channel slice of the input the (16+2)x(32+2) halo is staged ONCE in
+//       a CTA owns SR_TM side-by-side 16x8 pixel tiles (M = 128 rows = y*8+x each) that share every
+//       weight stage; per 32-channel slice of the input the (16+2)x(8*SR_TM+2) halo is staged ONCE in
 //       shared memory as four 8-channel planes
 //       [plane][hy][hx] x 16 B -- which IS the canonical K-major UMMA layout (core matrix = 8
 //       horizontally adjacent pixels, SBO = halo row pitch, LBO = plane pitch) -- so the nine taps
 //       are nine shared-memory descriptors that differ only in their start address
-//       (+dy*ROW + dx*16 B); weights are pre-packed per (slice, tap) as [N][32] K-major tiles;
+//       (+dy*ROW + dx*16 B); weights are pre-packed per (slice, tap) as [N][16] K-major tiles;
 //       fp32 accumulators live in TMEM for the whole K loop (9 taps x Cin/16 MMAs), loads of slice
 //       c+1 (cp.async, zero-fill = the conv's zero padding) overlap the MMAs of slice c;
 //       dense-block concatenation is free (a conv reads channels [0,Cin) of the block's NHWC buffer
@@ -68,14 +68,16 @@ __device__ __forceinline__ void cp_async16(void* dst_smem, const void* src, int 
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" :: "r"(sr_s32(dst_smem)), "l"(src), "r"(src_bytes) : "memory");
 }
 
-constexpr int SR_TM = 4;                             // M tiles (16x8 pixels each) per CTA, side by side in x:
-                                                     // they share one weight stage (4x less L2->smem weight traffic)
+constexpr int SR_TM = 1;                             // M tiles (16x8 pixels each) per CTA, side by side in x, sharing one
+                                                     // weight stage.  Measured: TM=4 (1 CTA/SM) 34.5 ms/frame vs TM=1
+                                                     // (2 CTAs/SM) 30.3 ms -- occupancy beats weight reuse here
 constexpr int SR_TY = 16, SR_TX = 8 * SR_TM;         // output region of a CTA (pixels)
 constexpr int SR_HY = SR_TY + 2, SR_HX = SR_TX + 2;  // halo
-constexpr int SR_ROW = SR_HX * 16;                   // 544 B: one halo row of one 8-channel plane
-constexpr int SR_PLANE = SR_HY * SR_ROW;             // 9792 B
-constexpr int SR_CK = 32;                            // input channels per K slice
-constexpr int SR_A_STAGE = (SR_CK / 8) * SR_PLANE;   // 39168 B
+constexpr int SR_ROW = SR_HX * 16;                   // 160 B (TM=1): one halo row of one 8-channel plane
+constexpr int SR_PLANE = SR_HY * SR_ROW;             // 2880 B (TM=1)
+constexpr int SR_CK = 16;                            // input channels per K slice (one k16 MMA step per tap): small
+                                                     // stages => 4 CTAs/SM whose load / MMA / epilogue phases overlap
+constexpr int SR_A_STAGE = (SR_CK / 8) * SR_PLANE;   // 11520 B (TM=1)
 
 enum { SRM_STORE_F16 = 0,      // dst_h[c0..c0+N) = act(acc + b)
        SRM_TRUNK = 1,          // dst_f = (acc + b) * scale + add_f                  (conv5: x5*0.2 + x)
@@ -128,8 +130,8 @@ __global__ void __launch_bounds__(128) conv3x3_tc_kernel(const __grid_constant__
         unsigned char* A = smem + st * STAGE;
         unsigned char* B = A + SR_A_STAGE;
         // halo: 180 pixels x 4 planes of 16 B
-        for (int i = tid; i < SR_HY * SR_HX * 4; i += 128) {
-            const int plane = i & 3, pix = i >> 2;
+        for (int i = tid; i < SR_HY * SR_HX * (SR_CK / 8); i += 128) {
+            const int plane = i % (SR_CK / 8), pix = i / (SR_CK / 8);
             const int hy = pix / SR_HX, hx = pix - hy * SR_HX;
             const int gy = y0 - 1 + hy, gx = x0 - 1 + hx;
             const bool in = (gy >= 0) & (gy < p.H) & (gx >= 0) & (gx < p.W);
@@ -575,20 +577,20 @@ __global__ void nchw_to_nhwc32_kernel(const float* __restrict__ src, __half* __r
     dst[i] = __float2half_rn(c < C ? src[(size_t)c * P + pix] : 0.f);
 }
 
-// conv weight [Cout][Cin][3][3] fp32 -> [cin_slice][tap][NPAD][32] canonical K-major fp16 tiles
+// conv weight [Cout][Cin][3][3] fp32 -> [cin_slice][tap][NPAD][SR_CK] canonical K-major fp16 tiles
 __global__ void pack_conv3x3_kernel(const float* __restrict__ W, unsigned char* __restrict__ dst,
                                     int cout, int cin, int npad, int nslices) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long total = (long long)nslices * 9 * npad * 32;
+    const long long total = (long long)nslices * 9 * npad * SR_CK;
     if (i >= total) return;
-    const int k = (int)(i & 31);
-    long long r = i >> 5;
+    const int k = (int)(i % SR_CK);
+    long long r = i / SR_CK;
     const int n = (int)(r % npad); r /= npad;
     const int t = (int)(r % 9);
     const int sl = (int)(r / 9);
-    const int ci = sl * 32 + k;
+    const int ci = sl * SR_CK + k;
     const float w = (n < cout && ci < cin) ? W[((size_t)n * cin + ci) * 9 + t] : 0.f;
-    const size_t off = ((size_t)sl * 9 + t) * (npad * 64) + tc_canon_off(n, k >> 3, 4) + (k & 7) * 2;
+    const size_t off = ((size_t)sl * 9 + t) * (npad * SR_CK * 2) + tc_canon_off(n, k >> 3, SR_CK / 8) + (k & 7) * 2;
     *reinterpret_cast<__half*>(dst + off) = __float2half_rn(w);
 }
 
@@ -626,16 +628,16 @@ int sr_alloc(k4_srnet* n, void** p, size_t bytes) {
 int make_conv(k4_srnet* n, SrConv& c, const float* w, const float* b, int cout, int cin, cudaStream_t s) {
     c.cout = cout;
     c.npad = cout <= 16 ? 16 : (cout <= 32 ? 32 : 64);
-    c.cin_pad = (cin + 31) / 32 * 32;
-    const int nsl = c.cin_pad / 32;
-    const size_t bytes = (size_t)nsl * 9 * c.npad * 64;
+    c.cin_pad = (cin + 31) / 32 * 32;              // activations are stored in multiples of 32 channels
+    const int nsl = c.cin_pad / SR_CK;
+    const size_t bytes = (size_t)nsl * 9 * c.npad * SR_CK * 2;
     int st = sr_alloc(n, (void**)&c.wpack, bytes);
     if (st) return st;
     st = sr_alloc(n, (void**)&c.bias, 64 * 4);
     if (st) return st;
     K4_CUDA_TRY(cudaMemsetAsync(c.bias, 0, 64 * 4, s));
     K4_CUDA_TRY(cudaMemcpyAsync(c.bias, b, (size_t)cout * 4, cudaMemcpyDeviceToDevice, s));
-    const long long total = (long long)nsl * 9 * c.npad * 32;
+    const long long total = (long long)nsl * 9 * c.npad * SR_CK;
     pack_conv3x3_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(w, c.wpack, cout, cin, c.npad, nsl);
     K4_CUDA_TRY(cudaGetLastError());
     return K4_OK;

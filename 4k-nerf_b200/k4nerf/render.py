@@ -102,3 +102,28 @@ def render_viewpoints_sr(model, render_poses, HW, Ks, ndc, render_kwargs,
             psnrs.append(-10. * np.log10(np.mean(np.square(rgb - gt_imgs[i]))))
     _post(rgbs, depths, bgmaps, render_video_flipy, render_video_rot90)
     return np.array(rgbs), np.array(depths), np.array(bgmaps), psnrs, viewdirs_all, np.array(rgb_features)
+
+
+@torch.no_grad()
+def render_frame_4k(model, net_sr, H, W, K, c2w, ndc, render_kwargs, test_tile=510, out_u8=False,
+                    flip_x=False, flip_y=False):
+    """One full 4K-NeRF frame, device resident: rays generated on the
+    device, one fused marcher launch at HxW, ``rgb_feature`` + ``depth`` handed to the VC-Decoder
+    without the numpy round trip of run_sr.py:130-133,1362-1367, x4 decode with the reference's tile
+    geometry (``--test_tile``), optional ``to8b`` quantisation (lib/utils.py:20) on the device.
+
+    Returns ``(sr [3,4H,4W] float32 in [0,1] or uint8 [4H,4W,3], lr dict)`` -- same values as
+    ``render_viewpoints_sr`` followed by ``SFTNet.tile_process`` and ``clamp(0,1)``."""
+    rays_o, rays_d, viewdirs = dvgo.get_rays_of_a_view(
+        H, W, K, torch.as_tensor(np.asarray(c2w), dtype=torch.float32), ndc,
+        inverse_y=render_kwargs['inverse_y'], flip_x=flip_x, flip_y=flip_y)
+    kw = dict(render_kwargs)
+    kw['render_depth'] = True
+    lr = model.render_rays(rays_o.view(-1, 3), rays_d.view(-1, 3), viewdirs.view(-1, 3), kw, image_hw=(H, W))
+    x = lr['rgb_marched'].view(H, W, 3).permute(2, 0, 1).unsqueeze(0).contiguous()    # unclamped, as run_sr.py:131
+    cond = lr['depth'].view(1, H, W)
+    sr = net_sr.tile_process(x, cond, tile_size=test_tile if test_tile else max(H, W), to_cpu=False)
+    sr = sr.squeeze(0).clamp_(0, 1)
+    if out_u8:
+        sr = (sr * 255).to(torch.uint8).permute(1, 2, 0).contiguous()     # to8b: (255*clip(x,0,1)).astype(uint8)
+    return sr, lr

@@ -73,3 +73,27 @@ def test_full_4k_nerf_chain_mpi_plus_decoder(cuda_device):
     c_ref = ref['depth'].movedim(-1, 0)
     sr_ref = sftnet.tile_process(sd, x_ref, c_ref, 16)
     assert pipeline.psnr(sr, sr_ref) >= 60.0
+
+
+def test_render_frame_4k_device_resident(cuda_device):
+    """f-1: the device-resident chain equals render_viewpoints_sr + tile_process + clamp."""
+    dev = cuda_device
+    st = make_state('cfgA', res=32, regime='fog')
+    m = model_from_state(st, dev)
+    sd = sftnet.random_state_dict(seed=3, scale=1.0)
+    net = k4nerf.SFTNet(3, 4, 64, 5, 32, 1)
+    net.load_state_dict(sd)
+    net = net.to(dev)
+    H, W = 20, 28
+    K, c2w = scenes.blender_camera(H, W)
+    kw = dict(scenes.RENDER_KW_DVGO)
+    sr, lr = render.render_frame_4k(m, net, H, W, K, c2w, False, kw, test_tile=16)
+    assert sr.shape == (3, 4 * H, 4 * W) and sr.is_cuda and float(sr.min()) >= 0 and float(sr.max()) <= 1
+    _, depths, _, _, _, feats = render.render_viewpoints_sr(m, np.array([c2w.numpy()]), np.array([[H, W]]), np.array([K]), False, kw)
+    x = torch.from_numpy(feats[0]).movedim(-1, 0).unsqueeze(0).to(dev)
+    cond = torch.from_numpy(depths[0]).movedim(-1, 0).to(dev)
+    ref = net.tile_process(x, cond, tile_size=16).squeeze(0).clamp(0, 1)
+    assert (sr.cpu() - ref).abs().max().item() < 2e-3
+    u8, _ = render.render_frame_4k(m, net, H, W, K, c2w, False, kw, test_tile=16, out_u8=True)
+    assert u8.dtype == torch.uint8 and u8.shape == (4 * H, 4 * W, 3)
+    assert (u8.cpu().float() - (ref * 255).floor().permute(1, 2, 0)).abs().max().item() <= 1

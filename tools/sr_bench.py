@@ -16,7 +16,9 @@ from oracle import pipeline, sftnet  # noqa: E402
 
 def main():
     dev = torch.device('cuda', 0)
-    H, W = (int(sys.argv[1]), int(sys.argv[2])) if len(sys.argv) > 2 else (756, 1008)
+    args = [a for a in sys.argv[1:] if not a.startswith('--')]
+    no_ref = '--no-ref' in sys.argv
+    H, W = (int(args[0]), int(args[1])) if len(args) > 1 else (756, 1008)
     iters = 3
     sd = sftnet.random_state_dict(seed=3, scale=1.0)
     net = k4nerf.SFTNet(3, 4, 64, 5, 32, 1)
@@ -39,6 +41,8 @@ def main():
     ms, out = timeit(lambda: net.tile_process(img, cond, 510, to_cpu=False))
     rec = {'what': 'k4nerf SFTNet.tile_process (tcgen05)', 'hw': [H, W], 'ms_per_frame': ms, 'tflops': flop / ms / 1e9}
     print(json.dumps(rec), flush=True)
+    if no_ref:
+        return
     sd_dev = {k: v.to(dev) for k, v in sd.items()}
     refs = {}
     for tf32 in (True, False):
