@@ -184,6 +184,51 @@ K4_API size_t k4_srnet_workspace_bytes(const k4_srnet* net, int32_t h, int32_t w
 K4_API int k4_srnet_forward(const k4_srnet* net, const float* d_x, const float* d_cond, int32_t h, int32_t w,
                             float* d_out, void* d_workspace, size_t workspace_bytes, k4_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Op-level surface: the 13 functions of the reference extension `render_utils_cuda`
+ * (lib/cuda/render_utils.cpp:170-184), bit-identical results, caller-allocated outputs, no host sync.
+ * Needed for training compatibility (lib/dvgo.py:453-511 autograd shims), not for inference.
+ * All pointers are device pointers; masks are bytes (torch.bool); ids are int64.
+ *   reference function                      entry point(s)
+ *   infer_t_minmax            (.cpp:50)     k4_op_infer_t_minmax
+ *   infer_n_samples           (.cpp:60)     k4_op_infer_n_samples
+ *   infer_ray_start_dir       (.cpp:68)     k4_op_infer_ray_start_dir
+ *   sample_pts_on_rays        (.cpp:76)     the three above + cumsum (host side) + k4_op_fill_ray_step_ids + k4_op_sample_pts
+ *   sample_ndc_pts_on_rays    (.cpp:92)     k4_op_sample_ndc_pts
+ *   sample_bg_pts_on_rays     (.cpp:104)    k4_op_sample_bg_pts
+ *   maskcache_lookup          (.cpp:112)    k4_op_maskcache_lookup       (out must be pre-zeroed, as .cu:405)
+ *   raw2alpha[_nonuni]        (.cpp:124,131) k4_op_raw2alpha             (interval_v = NULL | per-point intervals)
+ *   raw2alpha[_nonuni]_backward (.cpp:138,146) k4_op_raw2alpha_backward
+ *   alpha2weight              (.cpp:154)    k4_op_alpha2weight           (outputs pre-filled 0/1/1/0/0 as .cu:624-628)
+ *   alpha2weight_backward     (.cpp:162)    k4_op_alpha2weight_backward  (grad pre-zeroed as .cu:684)
+ */
+K4_API int k4_op_infer_t_minmax(const float* d_rays_o, const float* d_rays_d, const float* d_xyz_min, const float* d_xyz_max,
+                                float near_, float far_, int64_t n_rays, float* d_t_min, float* d_t_max, k4_stream_t stream);
+K4_API int k4_op_infer_n_samples(const float* d_rays_d, const float* d_t_min, const float* d_t_max, float stepdist, int64_t n_rays,
+                                 int64_t* d_n_samples, k4_stream_t stream);
+K4_API int k4_op_infer_ray_start_dir(const float* d_rays_o, const float* d_rays_d, const float* d_t_min, int64_t n_rays,
+                                     float* d_rays_start, float* d_rays_dir, k4_stream_t stream);
+K4_API int k4_op_fill_ray_step_ids(const int64_t* d_n_steps_cumsum, int64_t n_rays, int64_t total, int64_t* d_ray_id,
+                                   int64_t* d_step_id, k4_stream_t stream);
+K4_API int k4_op_sample_pts(const float* d_rays_start, const float* d_rays_dir, const float* d_xyz_min, const float* d_xyz_max,
+                            const int64_t* d_ray_id, const int64_t* d_step_id, float stepdist, int64_t total, float* d_pts,
+                            uint8_t* d_mask_outbbox, k4_stream_t stream);
+K4_API int k4_op_sample_ndc_pts(const float* d_rays_o, const float* d_rays_d, const float* d_xyz_min, const float* d_xyz_max,
+                                int32_t N_samples, int64_t n_rays, float* d_pts, uint8_t* d_mask_outbbox, k4_stream_t stream);
+K4_API int k4_op_sample_bg_pts(const float* d_rays_o, const float* d_rays_d, const float* d_t_max, float bg_preserve,
+                               int32_t N_samples, int64_t n_rays, float* d_pts, k4_stream_t stream);
+K4_API int k4_op_maskcache_lookup(const uint8_t* d_world, const float* d_xyz, uint8_t* d_out, const float* d_scale,
+                                  const float* d_shift, int32_t sz_i, int32_t sz_j, int32_t sz_k, int64_t n_pts, k4_stream_t stream);
+K4_API int k4_op_raw2alpha(const float* d_density, float shift, float interval, const float* d_interval_v, int64_t n_pts,
+                           float* d_exp, float* d_alpha, k4_stream_t stream);
+K4_API int k4_op_raw2alpha_backward(const float* d_exp, const float* d_grad_back, float interval, const float* d_interval_v,
+                                    int64_t n_pts, float* d_grad, k4_stream_t stream);
+K4_API int k4_op_alpha2weight(const float* d_alpha, const int64_t* d_ray_id, int64_t n_rays, int64_t n_pts, float* d_weight,
+                              float* d_T, float* d_alphainv_last, int64_t* d_i_start, int64_t* d_i_end, k4_stream_t stream);
+K4_API int k4_op_alpha2weight_backward(const float* d_alpha, const float* d_weight, const float* d_T, const float* d_alphainv_last,
+                                       const int64_t* d_i_start, const int64_t* d_i_end, int64_t n_rays,
+                                       const float* d_grad_weights, const float* d_grad_last, float* d_grad, k4_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
