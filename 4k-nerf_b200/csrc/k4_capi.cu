@@ -195,7 +195,7 @@ extern "C" size_t k4_scene_device_bytes(const k4_scene* sc) { return sc ? sc->by
 extern "C" int k4_scene_create(const k4_scene_desc* d, k4_stream_t stream, k4_scene** out) {
     if (!d || !out) return K4_ERR_INVALID_ARG;
     *out = nullptr;
-    if (d->kind != K4_KIND_DVGO && d->kind != K4_KIND_DMPIGO) return K4_ERR_INVALID_ARG;
+    if (d->kind != K4_KIND_DVGO && d->kind != K4_KIND_DMPIGO && d->kind != K4_KIND_DCVGO) return K4_ERR_INVALID_ARG;
     for (int a = 0; a < 3; ++a)
         if (d->world_size[a] < 2 || d->mask_size[a] < 1) return K4_ERR_INVALID_ARG;
     if (!d->d_density || !d->d_k0 || !d->d_mask) return K4_ERR_INVALID_ARG;
@@ -228,6 +228,9 @@ extern "C" int k4_scene_create(const k4_scene_desc* d, k4_stream_t stream, k4_sc
     v.max_world_size = d->max_world_size; v.mpi_depth = d->mpi_depth;
     v.depth = d->rgbnet_depth; v.width = d->rgbnet_width; v.direct = d->rgbnet_direct;
     v.viewpe = d->viewbase_pe; v.spape = d->spatial_pe;
+    for (int a = 0; a < 3; ++a) { v.scene_center[a] = d->scene_center[a]; v.scene_radius[a] = d->scene_radius[a]; }
+    v.bg_len = d->bg_len; v.one_plus_bg = (float)(1.0 + (double)d->bg_len); v.world_len = d->world_len;
+    if (d->kind == K4_KIND_DCVGO) v.direct = 1;
 
 #define K4_TRY(x) do { st = (x); if (st != K4_OK) { k4_scene_destroy(sc); return st; } } while (0)
 #define K4_CTRY(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) { k4_set_cuda_error(_e, #x); k4_scene_destroy(sc); return K4_ERR_CUDA; } } while (0)
@@ -257,6 +260,8 @@ extern "C" int k4_scene_create(const k4_scene_desc* d, k4_stream_t stream, k4_sc
         if (d->kind == K4_KIND_DVGO) {
             v.k0_view_off = v.direct ? 0 : 3;
             dim0 += v.C - v.k0_view_off;                          // lib/dvgo.py:94-101
+        } else if (d->kind == K4_KIND_DCVGO) {
+            dim0 += v.C;                                          // lib/dcvgo.py:105-106
         } else {
             dim0 += 3 + 3 * v.spape * 2 + v.C;                    // lib/dmpigo.py:85
         }
@@ -354,6 +359,14 @@ extern "C" int k4_render_rays(const k4_scene* sc, const k4_render_args* a,
         rp.stepdist = a->stepsize * v.voxel_size;                   // lib/dvgo.py:310 (fp32 product)
         rp.interval = a->stepsize * v.voxel_size_ratio;             // lib/dvgo.py:341 (fp32 product)
         rp.n_samples = (int)((float)(v.max_world_size - 1) / a->stepsize) + 1;   // lib/dvgo.py:311
+    } else if (v.kind == K4_KIND_DCVGO) {
+        if (!a->d_t_list || a->n_t < 2) return K4_ERR_INVALID_ARG;
+        rp.far_ = a->far_;
+        rp.stepdist = 0.f;
+        rp.interval = a->stepsize * v.voxel_size_ratio;             // lib/dcvgo.py:279 (fp32 product)
+        rp.n_samples = a->n_t;                                      // n_max = len(t)
+        rp.t_list = a->d_t_list;
+        rp.dist_thres = a->dist_thres;
     } else {
         if (!(a->near_ == 0.f && a->far_ == 1.f)) return K4_ERR_INVALID_ARG;      // lib/dmpigo.py:275
         rp.far_ = a->far_;
@@ -374,8 +387,8 @@ extern "C" int k4_render_rays(const k4_scene* sc, const k4_render_args* a,
     rp.tile_counter = reinterpret_cast<unsigned int*>(d_workspace);
     K4_CUDA_TRY(cudaMemsetAsync(d_workspace, 0, 16, s));
     if ((a->mlp_mode == K4_MLP_TCGEN05 || a->mlp_mode == K4_MLP_TCGEN05_WS) && v.depth > 0) {
-        if (!k4_tc_supported(v)) return K4_ERR_UNSUPPORTED;
-        return a->mlp_mode == K4_MLP_TCGEN05 ? k4_launch_march_tc(sc, rp, s) : k4_launch_march_ws(sc, rp, s);
+        if (a->mlp_mode == K4_MLP_TCGEN05) return k4_tc_supported(v) ? k4_launch_march_tc(sc, rp, s) : K4_ERR_UNSUPPORTED;
+        return k4_ws_supported(v) ? k4_launch_march_ws(sc, rp, s) : K4_ERR_UNSUPPORTED;
     }
     return k4_launch_march(sc, rp, a->mlp_mode, s);
 }

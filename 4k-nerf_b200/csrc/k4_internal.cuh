@@ -35,6 +35,9 @@ struct K4Dev {
     // tcgen05 pack: one blob of canonical K-major (no swizzle) UMMA operand tiles, see tc_blob_layout()
     const unsigned char* tc_blob;
     int tc_kpad, tc_width;
+    // DirectContractedVoxGO (lib/dcvgo.py)
+    float scene_center[3], scene_radius[3], bg_len, one_plus_bg;
+    int world_len;
 };
 
 // ---- tcgen05 operand blob (built by k4_scene_create, staged by one TMA bulk copy) -----------------
@@ -73,6 +76,8 @@ struct k4_scene {
 
 struct K4RenderParams {
     float near_, far_, stepdist, interval, bg, inv_nsamples;
+    const float* t_list;          // DCVGO: per-step ray parameter (device, n_samples entries)
+    float dist_thres;             // DCVGO: cumdist_thres threshold (lib/dcvgo.py:283)
     int n_samples;                // MPI: samples per ray; DVGO: depth normaliser only
     int render_depth;
     int image_w, image_h;         // >0: 2-D 8x4 tiles
@@ -102,4 +107,5 @@ void k4_set_cuda_error(cudaError_t e, const char* where);
 int k4_launch_march(const k4_scene* sc, const K4RenderParams& rp, int mlp_mode, cudaStream_t st);
 int k4_launch_march_tc(const k4_scene* sc, K4RenderParams rp, cudaStream_t st);   // K4_ERR_UNSUPPORTED if the shape has no tcgen05 build
 bool k4_tc_supported(const K4Dev& v);
+bool k4_ws_supported(const K4Dev& v);
 int k4_launch_march_ws(const k4_scene* sc, K4RenderParams rp, cudaStream_t st);   // warp-specialised variant (same shapes)

@@ -109,6 +109,14 @@ k4_march_kernel(const __grid_constant__ K4Dev s, const __grid_constant__ K4Rende
             const Vec3 o = ld3(rp.rays_o, ray_i), d = ld3(rp.rays_d, ray_i);
             if (KIND == K4_KIND_DVGO) {
                 r = setup_ray_dvgo(s, rp, o, d);
+            } else if (KIND == K4_KIND_DCVGO) {
+                // sample_ray, lib/dcvgo.py:237-238: o' = (o - center) / radius ; d' = d / ||d||  (torch ops)
+                r.sx = __fdiv_rn(__fsub_rn(o.x, s.scene_center[0]), s.scene_radius[0]);
+                r.sy = __fdiv_rn(__fsub_rn(o.y, s.scene_center[1]), s.scene_radius[1]);
+                r.sz = __fdiv_rn(__fsub_rn(o.z, s.scene_center[2]), s.scene_radius[2]);
+                const float dn = l2norm3_aten(d.x, d.y, d.z);
+                r.dx = __fdiv_rn(d.x, dn); r.dy = __fdiv_rn(d.y, dn); r.dz = __fdiv_rn(d.z, dn);
+                r.n_steps = rp.n_samples;
             } else {
                 r.sx = o.x; r.sy = o.y; r.sz = o.z; r.dx = d.x; r.dy = d.y; r.dz = d.z;
                 r.n_steps = rp.n_samples;
@@ -126,6 +134,7 @@ k4_march_kernel(const __grid_constant__ K4Dev s, const __grid_constant__ K4Rende
         int cnt_m = 0, cnt_d = 0, cnt_c = 0;
         bool done = !have_ray;
         const float mpi_den = (float)(rp.n_samples - 1);
+        float cum_dist = 0.f, qx = 0.f, qy = 0.f, qz = 0.f;      // DCVGO: cumdist_thres state, previous contracted point
 
         for (int i = 0; ; ++i) {
             const bool active = !done && (i < r.n_steps);
@@ -142,14 +151,43 @@ k4_march_kernel(const __grid_constant__ K4Dev s, const __grid_constant__ K4Rende
                     px = __fmaf_rn(r.dx, dist, r.sx);
                     py = __fmaf_rn(r.dy, dist, r.sy);
                     pz = __fmaf_rn(r.dz, dist, r.sz);
-                } else {
+                } else if (KIND == K4_KIND_DMPIGO) {
                     const float dist = __fdiv_rn((float)i, mpi_den);
                     px = __fmaf_rn(r.dx, dist, r.sx);
                     py = __fmaf_rn(r.dy, dist, r.sy);
                     pz = __fmaf_rn(r.dz, dist, r.sz);
                 }
-                const bool outb = (s.xyz_min[0] > px) | (s.xyz_min[1] > py) | (s.xyz_min[2] > pz) |
-                                  (s.xyz_max[0] < px) | (s.xyz_max[1] < py) | (s.xyz_max[2] < pz);
+                bool outb;
+                float t_i = 0.f;
+                if (KIND == K4_KIND_DCVGO) {
+                    // lib/dcvgo.py:249-262: p = o' + d'*t (separate torch ops), inf-norm contraction of the outside
+                    t_i = __ldg(rp.t_list + i);
+                    px = __fadd_rn(r.sx, __fmul_rn(r.dx, t_i));
+                    py = __fadd_rn(r.sy, __fmul_rn(r.dy, t_i));
+                    pz = __fadd_rn(r.sz, __fmul_rn(r.dz, t_i));
+                    const float nrm = fmaxf(fabsf(px), fmaxf(fabsf(py), fabsf(pz)));
+                    const bool inner = nrm <= 1.f;
+                    if (!inner) {
+                        // ray_pts / norm * ((1+bg_len) - bg_len/norm); scalar/tensor is reciprocal()*scalar
+                        const float f = __fsub_rn(s.one_plus_bg, __fmul_rn(__fdiv_rn(1.f, nrm), s.bg_len));
+                        px = __fmul_rn(__fdiv_rn(px, nrm), f);
+                        py = __fmul_rn(__fdiv_rn(py, nrm), f);
+                        pz = __fmul_rn(__fdiv_rn(pz, nrm), f);
+                    }
+                    // lib/dcvgo.py:282-285 + ub360_utils_kernel.cu:12-32: keep inner points, and outer points
+                    // whenever the distance accumulated since the last kept-by-distance point exceeds thres
+                    bool over = false;
+                    if (i > 0) {
+                        cum_dist = __fadd_rn(cum_dist, l2norm3_aten(__fsub_rn(px, qx), __fsub_rn(py, qy), __fsub_rn(pz, qz)));
+                        over = cum_dist > rp.dist_thres;
+                        if (over) cum_dist = 0.f;
+                    }
+                    qx = px; qy = py; qz = pz;
+                    outb = !(inner | over);
+                } else {
+                    outb = (s.xyz_min[0] > px) | (s.xyz_min[1] > py) | (s.xyz_min[2] > pz) |
+                           (s.xyz_max[0] < px) | (s.xyz_max[1] < py) | (s.xyz_max[2] < pz);
+                }
                 if (!outb) {
                     ++cnt_m;
                     // MaskGrid.forward -> maskcache_lookup (render_utils_kernel.cu:385-390)
@@ -186,9 +224,13 @@ k4_march_kernel(const __grid_constant__ K4Dev s, const __grid_constant__ K4Rende
                                 shade = true;
                                 w_sample = w;
                                 ++cnt_c;
-                                if (rp.render_depth)
-                                    acc_depth = __fadd_rn(acc_depth,
-                                        __fmul_rn(w, __fmul_rn(__fadd_rn((float)i, 0.5f), rp.inv_nsamples)));
+                                if (rp.render_depth) {
+                                    // DVGO/MPI: s = (step + 0.5) / N_samples; DCVGO: s = 1 - 1/(1+t)  (lib/dcvgo.py:353)
+                                    const float sd = (KIND == K4_KIND_DCVGO)
+                                        ? __fsub_rn(1.f, __fdiv_rn(1.f, __fadd_rn(1.f, t_i)))
+                                        : __fmul_rn(__fadd_rn((float)i, 0.5f), rp.inv_nsamples);
+                                    acc_depth = __fadd_rn(acc_depth, __fmul_rn(w, sd));
+                                }
                             }
                         }
                     }
@@ -283,6 +325,13 @@ int launch_variant(const k4_scene* sc, const K4RenderParams& rp, cudaStream_t st
 }  // namespace
 
 int k4_launch_march(const k4_scene* sc, const K4RenderParams& rp, int mlp_mode, cudaStream_t st) {
+    if (sc->dev.kind == K4_KIND_DCVGO) {
+        if (mlp_mode == K4_MLP_FP32 || sc->dev.depth == 0) return launch_variant<K4_KIND_DCVGO, K4_MLP_FP32>(sc, rp, st);
+        if (!MmaWarpCtx<K4_MLP_F16>::supported(sc->dev)) return K4_ERR_UNSUPPORTED;
+        if (mlp_mode == K4_MLP_F16) return launch_variant<K4_KIND_DCVGO, K4_MLP_F16>(sc, rp, st);
+        if (mlp_mode == K4_MLP_F16X3) return launch_variant<K4_KIND_DCVGO, K4_MLP_F16X3>(sc, rp, st);
+        return K4_ERR_UNSUPPORTED;
+    }
     const bool mpi = sc->dev.kind == K4_KIND_DMPIGO;
     if (mlp_mode == K4_MLP_FP32 || sc->dev.depth == 0) {
         return mpi ? launch_variant<K4_KIND_DMPIGO, K4_MLP_FP32>(sc, rp, st)

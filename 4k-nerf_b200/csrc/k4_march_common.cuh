@@ -127,6 +127,15 @@ __device__ __forceinline__ void interp_k0(const K4Dev& s, const float w[8], cons
     }
 }
 
+// torch.norm(dim=-1) of a 3-vector on CUDA: the reduction accumulates acc = fma(x, x, acc) in element
+// order from 0, then sqrt (ATen norm_two ops compiled with fmad).
+__device__ __forceinline__ float l2norm3_aten(float x, float y, float z) {
+    float s = __fmul_rn(x, x);
+    s = __fmaf_rn(y, y, s);
+    s = __fmaf_rn(z, z, s);
+    return __fsqrt_rn(s);
+}
+
 // torch.sigmoid on CUDA: 1 / (1 + exp(-x)) in fp32.
 __device__ __forceinline__ float sigmoid_ref(float x) {
     return __fdiv_rn(1.f, __fadd_rn(1.f, expf(-x)));

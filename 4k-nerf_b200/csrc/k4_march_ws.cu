@@ -382,6 +382,14 @@ k4_march_ws_kernel(const __grid_constant__ K4Dev s, const __grid_constant__ K4Re
                     r.n_steps = (ns > 1.f) ? ((ns >= 2147483520.f) ? 2147483647 : (int)ns) : 1;
                     r.sx = __fmaf_rn(d.x, r.t_min, o.x); r.sy = __fmaf_rn(d.y, r.t_min, o.y); r.sz = __fmaf_rn(d.z, r.t_min, o.z);
                     r.dx = __fdiv_rn(d.x, rnorm); r.dy = __fdiv_rn(d.y, rnorm); r.dz = __fdiv_rn(d.z, rnorm);
+                } else if (Cfg::KIND == K4_KIND_DCVGO) {
+                    // sample_ray, lib/dcvgo.py:237-238 (see k4_march.cu for the derivation)
+                    r.sx = __fdiv_rn(__fsub_rn(o.x, s.scene_center[0]), s.scene_radius[0]);
+                    r.sy = __fdiv_rn(__fsub_rn(o.y, s.scene_center[1]), s.scene_radius[1]);
+                    r.sz = __fdiv_rn(__fsub_rn(o.z, s.scene_center[2]), s.scene_radius[2]);
+                    const float dn = l2norm3_aten(d.x, d.y, d.z);
+                    r.dx = __fdiv_rn(d.x, dn); r.dy = __fdiv_rn(d.y, dn); r.dz = __fdiv_rn(d.z, dn);
+                    r.n_steps = rp.n_samples;
                 } else {
                     r.sx = o.x; r.sy = o.y; r.sz = o.z; r.dx = d.x; r.dy = d.y; r.dz = d.z;
                     r.n_steps = rp.n_samples;
@@ -407,6 +415,7 @@ k4_march_ws_kernel(const __grid_constant__ K4Dev s, const __grid_constant__ K4Re
             int cnt_m = 0, cnt_d = 0, cnt_c = 0;
             bool done = !have_ray;
             int i = 0;
+            float cum_dist = 0.f, qx = 0.f, qy = 0.f, qz = 0.f;      // DCVGO: cumdist_thres state, previous point
 
             for (;;) {
 #pragma unroll 1
@@ -427,12 +436,38 @@ k4_march_ws_kernel(const __grid_constant__ K4Dev s, const __grid_constant__ K4Re
                         if (Cfg::KIND == K4_KIND_DVGO) {
                             const float dist = __fmul_rn(rp.stepdist, (float)i);
                             px = __fmaf_rn(r.dx, dist, r.sx); py = __fmaf_rn(r.dy, dist, r.sy); pz = __fmaf_rn(r.dz, dist, r.sz);
-                        } else {
+                        } else if (Cfg::KIND == K4_KIND_DMPIGO) {
                             const float dist = __fdiv_rn((float)i, mpi_den);
                             px = __fmaf_rn(r.dx, dist, r.sx); py = __fmaf_rn(r.dy, dist, r.sy); pz = __fmaf_rn(r.dz, dist, r.sz);
                         }
-                        const bool outb = (s.xyz_min[0] > px) | (s.xyz_min[1] > py) | (s.xyz_min[2] > pz) |
-                                          (s.xyz_max[0] < px) | (s.xyz_max[1] < py) | (s.xyz_max[2] < pz);
+                        bool outb;
+                        float t_i = 0.f;
+                        if (Cfg::KIND == K4_KIND_DCVGO) {
+                            // lib/dcvgo.py:249-262,282-285: contracted sample + cumdist_thres (as k4_march.cu)
+                            t_i = __ldg(rp.t_list + i);
+                            px = __fadd_rn(r.sx, __fmul_rn(r.dx, t_i));
+                            py = __fadd_rn(r.sy, __fmul_rn(r.dy, t_i));
+                            pz = __fadd_rn(r.sz, __fmul_rn(r.dz, t_i));
+                            const float nrm = fmaxf(fabsf(px), fmaxf(fabsf(py), fabsf(pz)));
+                            const bool inner = nrm <= 1.f;
+                            if (!inner) {
+                                const float f = __fsub_rn(s.one_plus_bg, __fmul_rn(__fdiv_rn(1.f, nrm), s.bg_len));
+                                px = __fmul_rn(__fdiv_rn(px, nrm), f);
+                                py = __fmul_rn(__fdiv_rn(py, nrm), f);
+                                pz = __fmul_rn(__fdiv_rn(pz, nrm), f);
+                            }
+                            bool over = false;
+                            if (i > 0) {
+                                cum_dist = __fadd_rn(cum_dist, l2norm3_aten(__fsub_rn(px, qx), __fsub_rn(py, qy), __fsub_rn(pz, qz)));
+                                over = cum_dist > rp.dist_thres;
+                                if (over) cum_dist = 0.f;
+                            }
+                            qx = px; qy = py; qz = pz;
+                            outb = !(inner | over);
+                        } else {
+                            outb = (s.xyz_min[0] > px) | (s.xyz_min[1] > py) | (s.xyz_min[2] > pz) |
+                                   (s.xyz_max[0] < px) | (s.xyz_max[1] < py) | (s.xyz_max[2] < pz);
+                        }
                         if (!outb) {
                             ++cnt_m;
                             const int mi = (int)roundf(__fmaf_rn(px, s.m_scale[0], s.m_shift[0]));
@@ -465,8 +500,12 @@ k4_march_ws_kernel(const __grid_constant__ K4Dev s, const __grid_constant__ K4Re
                                         shade = true;
                                         w_sample = w;
                                         ++cnt_c;
-                                        if (rp.render_depth)
-                                            acc_depth = __fadd_rn(acc_depth, __fmul_rn(w, __fmul_rn(__fadd_rn((float)i, 0.5f), rp.inv_nsamples)));
+                                        if (rp.render_depth) {
+                                            const float sd = (Cfg::KIND == K4_KIND_DCVGO)
+                                                ? __fsub_rn(1.f, __fdiv_rn(1.f, __fadd_rn(1.f, t_i)))
+                                                : __fmul_rn(__fadd_rn((float)i, 0.5f), rp.inv_nsamples);
+                                            acc_depth = __fadd_rn(acc_depth, __fmul_rn(w, sd));
+                                        }
                                     }
                                 }
                             }
@@ -586,6 +625,7 @@ int launch_ws(const k4_scene* sc, K4RenderParams rp, cudaStream_t st) {
 
 using CfgA = TcCfg<K4_KIND_DVGO, 12, 4, 0, 128>;    // configs/default.py:107-119 fine stage
 using CfgB = TcCfg<K4_KIND_DMPIGO, 9, 0, 0, 64>;    // configs/llff/llff_default_lg.py + fern_lg_joint_l1.py
+using CfgC = TcCfg<K4_KIND_DCVGO, 12, 4, 0, 128>;   // lib/dcvgo.py with the fine-stage colour net (same MLP as CfgA)
 
 template <class Cfg>
 bool matches(const K4Dev& v) {
@@ -599,5 +639,8 @@ bool matches(const K4Dev& v) {
 int k4_launch_march_ws(const k4_scene* sc, K4RenderParams rp, cudaStream_t st) {
     if (matches<CfgA>(sc->dev)) return launch_ws<CfgA>(sc, rp, st);
     if (matches<CfgB>(sc->dev)) return launch_ws<CfgB>(sc, rp, st);
+    if (matches<CfgC>(sc->dev)) return launch_ws<CfgC>(sc, rp, st);
     return K4_ERR_UNSUPPORTED;
 }
+
+bool k4_ws_supported(const K4Dev& v) { return matches<CfgA>(v) || matches<CfgB>(v) || matches<CfgC>(v); }

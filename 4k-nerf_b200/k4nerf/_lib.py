@@ -6,7 +6,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libk4nerf.so')
 
 K4_OK = 0
-K4_KIND_DVGO, K4_KIND_DMPIGO = 0, 1
+K4_KIND_DVGO, K4_KIND_DMPIGO, K4_KIND_DCVGO = 0, 1, 2
 K4_MLP_FP32, K4_MLP_F16, K4_MLP_F16X3, K4_MLP_TCGEN05, K4_MLP_TCGEN05_WS = 0, 1, 2, 3, 4
 K4_MAX_MLP_LAYERS = 8
 MLP_MODES = {'fp32': K4_MLP_FP32, 'f16': K4_MLP_F16, 'f16x3': K4_MLP_F16X3, 'tcgen05': K4_MLP_TCGEN05,
@@ -25,6 +25,7 @@ class SceneDesc(C.Structure):
         ('viewbase_pe', C.c_int32), ('spatial_pe', C.c_int32), ('reserved0', C.c_int32),
         ('d_density', C.c_void_p), ('d_k0', C.c_void_p), ('d_mask', C.c_void_p), ('d_act_shift_grid', C.c_void_p),
         ('d_rgbnet_weight', C.c_void_p * K4_MAX_MLP_LAYERS), ('d_rgbnet_bias', C.c_void_p * K4_MAX_MLP_LAYERS),
+        ('scene_center', C.c_float * 3), ('scene_radius', C.c_float * 3), ('bg_len', C.c_float), ('world_len', C.c_int32),
     ]
 
 
@@ -32,6 +33,7 @@ class RenderArgs(C.Structure):
     _fields_ = [
         ('near_', C.c_float), ('far_', C.c_float), ('stepsize', C.c_float), ('bg', C.c_float),
         ('render_depth', C.c_int32), ('mlp_mode', C.c_int32), ('image_w', C.c_int32), ('image_h', C.c_int32),
+        ('d_t_list', C.c_void_p), ('n_t', C.c_int32), ('dist_thres', C.c_float),
     ]
 
 

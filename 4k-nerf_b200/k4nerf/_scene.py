@@ -88,6 +88,11 @@ def build_scene(kind, module, extra):
     d.rgbnet_direct = int(bool(extra.get('rgbnet_direct', True)))
     d.viewbase_pe = int(extra.get('viewbase_pe', 0))
     d.spatial_pe = int(extra.get('spatial_pe', 0))
+    if 'scene_center' in extra:
+        d.scene_center[:] = extra['scene_center']
+        d.scene_radius[:] = extra['scene_radius']
+        d.bg_len = float(extra['bg_len'])
+        d.world_len = int(extra['world_len'])
     keep = []
 
     def dptr(t, dtype):
@@ -119,6 +124,9 @@ class FusedRenderMixin:
     def _scene_extra(self):
         raise NotImplementedError
 
+    def _extra_render_args(self, a, render_kwargs, device, keep):
+        """Hook for model-specific k4_render_args fields (DirectContractedVoxGO's step list)."""
+
     def _get_scene(self):
         h = getattr(self, '_k4_handle', None)
         extra = self._scene_extra()
@@ -141,7 +149,7 @@ class FusedRenderMixin:
         vpe = int(getattr(self, 'viewbase_pe', 0))
         spe = int(getattr(self, 'spatial_pe', 0))
         if len(layers) == 3:
-            if self._k4_kind == _lib.K4_KIND_DVGO and C == 12 and vpe == 4 and width == 128 and getattr(self, 'rgbnet_direct', True):
+            if self._k4_kind in (_lib.K4_KIND_DVGO, _lib.K4_KIND_DCVGO) and C == 12 and vpe == 4 and width == 128 and getattr(self, 'rgbnet_direct', True):
                 return 'ws'
             if self._k4_kind == _lib.K4_KIND_DMPIGO and C == 9 and vpe == 0 and spe == 0 and width == 64:
                 return 'ws'
@@ -177,6 +185,8 @@ class FusedRenderMixin:
         a.mlp_mode = _lib.MLP_MODES[self.resolve_mlp_mode(mlp_mode or self.mlp_mode)]
         if image_hw is not None and image_hw[0] * image_hw[1] == N:
             a.image_h, a.image_w = int(image_hw[0]), int(image_hw[1])
+        keep = []
+        self._extra_render_args(a, render_kwargs, dev, keep)
         o = _lib.RenderOut()
         o.d_rgb_marched = rgb.data_ptr()
         o.d_alphainv_last = alphainv.data_ptr()

@@ -47,8 +47,9 @@ typedef void* k4_stream_t;                 /* cudaStream_t */
 typedef struct k4_scene k4_scene;          /* opaque: device-resident, repacked scene     */
 typedef struct k4_srnet k4_srnet;          /* opaque: device-resident VC-Decoder weights  */
 
-enum { K4_KIND_DVGO = 0,                   /* DirectVoxGO,  lib/dvgo.py:23-448   */
-       K4_KIND_DMPIGO = 1 };               /* DirectMPIGO,  lib/dmpigo.py:18-427 */
+enum { K4_KIND_DVGO = 0,                   /* DirectVoxGO,            lib/dvgo.py:23-448   */
+       K4_KIND_DMPIGO = 1,                 /* DirectMPIGO,            lib/dmpigo.py:18-427 */
+       K4_KIND_DCVGO = 2 };                /* DirectContractedVoxGO,  lib/dcvgo.py:27-382  */
 
 enum { K4_MLP_FP32 = 0,                    /* fp32 FFMA, sequential accumulation (exact mode)   */
        K4_MLP_F16 = 1,                     /* tensor cores, fp16 operands, fp32 accumulate       */
@@ -94,6 +95,11 @@ typedef struct k4_scene_desc {
     const float* d_act_shift_grid;/* MPI: [mpi_depth]; DVGO: NULL                               */
     const float* d_rgbnet_weight[K4_MAX_MLP_LAYERS]; /* [out,in] row major                      */
     const float* d_rgbnet_bias[K4_MAX_MLP_LAYERS];   /* [out]                                   */
+    /* DirectContractedVoxGO only (lib/dcvgo.py:46-55,226-248): xyz_min/max above are -+(1+bg_len)  */
+    float scene_center[3];        /* (xyz_min + xyz_max) / 2 of the foreground cube              */
+    float scene_radius[3];        /* (xyz_max - xyz_min) / 2                                     */
+    float bg_len;                 /* thickness of the contracted background shell                */
+    int32_t world_len;            /* world_size[0]                                               */
 } k4_scene_desc;
 
 /* render_kwargs of the reference forward (run_sr.py:1311-1320; lib/dvgo.py:327) + kernel knobs. */
@@ -106,6 +112,12 @@ typedef struct k4_render_args {
     int32_t mlp_mode;             /* K4_MLP_*                                                   */
     int32_t image_w;              /* >0: rays are a row-major HxW image -> 8x4 pixel tiles/warp */
     int32_t image_h;
+    /* DirectContractedVoxGO only: the per-step ray parameters `t` of sample_ray (lib/dcvgo.py:241-248,
+     * a function of world_len, bg_len and stepsize only; the host computes them with the reference's
+     * own torch expressions) and the cumdist_thres threshold (lib/dcvgo.py:283) */
+    const float* d_t_list;
+    int32_t n_t;
+    float dist_thres;
 } k4_render_args;
 
 typedef struct k4_render_out {

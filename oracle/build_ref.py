@@ -34,34 +34,41 @@ REF = '/root/reference/lib/cuda'
 HERE = os.path.dirname(os.path.abspath(__file__))
 OUT_DIR = os.path.join(HERE, '_ref')
 OUT_SO = os.path.join(OUT_DIR, 'render_utils_cuda.so')
+OUT_UB360 = os.path.join(OUT_DIR, 'ub360_utils_cuda.so')      # cumdist_thres of DirectContractedVoxGO
+MODULES = {
+    'render_utils_cuda': (('render_utils.cpp', 'render_utils_kernel.cu'), OUT_SO),
+    'ub360_utils_cuda': (('ub360_utils.cpp', 'ub360_utils_kernel.cu'), OUT_UB360),
+}
+
+
+def _build_one(name, files, out_so, verbose):
+    work = tempfile.mkdtemp(prefix='k4_refbuild_')
+    srcs = []
+    for fn in files:
+        with open(os.path.join(REF, fn)) as f:
+            text = f.read()
+        text = re.sub(r'(AT_DISPATCH_FLOATING_TYPES\(\s*[A-Za-z_0-9]+)\.type\(\)', r'\1.scalar_type()', text)
+        dst = os.path.join(work, fn)
+        with open(dst, 'w') as f:
+            f.write(text)
+        srcs.append(dst)
+    from torch.utils.cpp_extension import load
+    bdir = os.path.join(work, 'build')
+    os.makedirs(bdir)
+    load(name=name, sources=srcs, build_directory=bdir, verbose=verbose, is_python_module=False)
+    shutil.copyfile(os.path.join(bdir, name + '.so'), out_so)
+    shutil.rmtree(work, ignore_errors=True)
 
 
 def build(force=False, verbose=False):
     if not os.path.isdir(REF):
         return OUT_SO if os.path.exists(OUT_SO) else None
-    if os.path.exists(OUT_SO) and not force:
-        return OUT_SO
     os.makedirs(OUT_DIR, exist_ok=True)
-    work = tempfile.mkdtemp(prefix='k4_refbuild_')
-    srcs = []
-    for name in ('render_utils.cpp', 'render_utils_kernel.cu'):
-        with open(os.path.join(REF, name)) as f:
-            text = f.read()
-        text = re.sub(r'(AT_DISPATCH_FLOATING_TYPES\(\s*[A-Za-z_0-9]+)\.type\(\)', r'\1.scalar_type()', text)
-        dst = os.path.join(work, name)
-        with open(dst, 'w') as f:
-            f.write(text)
-        srcs.append(dst)
     os.environ.setdefault('TORCH_CUDA_ARCH_LIST', '10.0a')
     os.environ.setdefault('MAX_JOBS', str(os.cpu_count() or 4))
-    from torch.utils.cpp_extension import load
-    bdir = os.path.join(work, 'build')
-    os.makedirs(bdir)
-    load(name='render_utils_cuda', sources=srcs, build_directory=bdir, verbose=verbose,
-         is_python_module=False)
-    built = os.path.join(bdir, 'render_utils_cuda.so')
-    shutil.copyfile(built, OUT_SO)
-    shutil.rmtree(work, ignore_errors=True)
+    for name, (files, out_so) in MODULES.items():
+        if force or not os.path.exists(out_so):
+            _build_one(name, files, out_so, verbose)
     return OUT_SO
 
 

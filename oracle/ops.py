@@ -157,25 +157,35 @@ class CpuOps:
         return [weight, T, last, i_start, i_end]
 
 
+    @staticmethod
+    def cumdist_thres(dist, thres):
+        """ub360_utils_cuda.cumdist_thres (lib/cuda/ub360_utils.cpp:20-22)."""
+        dist = _f32(dist)
+        mask = torch.zeros(dist.shape, dtype=torch.bool)
+        if dist.numel():
+            _lib().k4o_cumdist_thres(_p(dist), ctypes.c_float(float(thres)), ctypes.c_int64(dist.shape[0]),
+                                     ctypes.c_int64(dist.shape[1]), _p(mask))
+        return mask
+
+
 def ref_ext_path():
     return os.path.join(HERE, '_ref', 'render_utils_cuda.so')
 
 
-_REF_MOD = None
+_REF_MODS = {}
 
 
-def load_ref_ext():
-    """Import oracle/_ref/render_utils_cuda.so (the reference's own pybind module)."""
-    global _REF_MOD
-    if _REF_MOD is None:
-        path = ref_ext_path()
+def load_ref_ext(name='render_utils_cuda'):
+    """Import oracle/_ref/<name>.so (the reference's own pybind module)."""
+    if name not in _REF_MODS:
+        path = os.path.join(HERE, '_ref', name + '.so')
         if not os.path.exists(path):
             raise FileNotFoundError(f'{path} missing: run `python oracle/build_ref.py` where /root/reference exists')
-        spec = importlib.util.spec_from_file_location('render_utils_cuda', path)
+        spec = importlib.util.spec_from_file_location(name, path)
         mod = importlib.util.module_from_spec(spec)
         spec.loader.exec_module(mod)
-        _REF_MOD = mod
-    return _REF_MOD
+        _REF_MODS[name] = mod
+    return _REF_MODS[name]
 
 
 class RefExtOps:
@@ -188,6 +198,10 @@ class RefExtOps:
 
     def __init__(self):
         self.m = load_ref_ext()
+
+    def cumdist_thres(self, dist, thres):
+        """ub360_utils_cuda.cumdist_thres -- the reference's own kernel (lib/dcvgo.py:284)."""
+        return load_ref_ext('ub360_utils_cuda').cumdist_thres(dist, thres)
 
     def __getattr__(self, name):
         return getattr(self.m, name)

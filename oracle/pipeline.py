@@ -120,6 +120,43 @@ def dmpigo_state(xyz_min, xyz_max, num_voxels, mpi_depth, fast_color_thres,
     return st
 
 
+def dcvgo_state(xyz_min, xyz_max, num_voxels, num_voxels_base, alpha_init, fast_color_thres, bg_len=0.2,
+                rgbnet_dim=0, rgbnet_depth=3, rgbnet_width=128, viewbase_pe=4, mask_cache_world_size=None):
+    """Shapes and derived scalars of DirectContractedVoxGO.__init__ (lib/dcvgo.py:28-128)."""
+    st = {'kind': 'dcvgo', 'bg_len': bg_len}
+    xyz_min = torch.Tensor(xyz_min)
+    xyz_max = torch.Tensor(xyz_max)
+    st['scene_center'] = (xyz_min + xyz_max) * 0.5
+    st['scene_radius'] = (xyz_max - xyz_min) * 0.5
+    st['xyz_min'] = torch.Tensor([-1, -1, -1]) - bg_len
+    st['xyz_max'] = torch.Tensor([1, 1, 1]) + bg_len
+    st['fast_color_thres'] = fast_color_thres
+    st['voxel_size_base'] = ((st['xyz_max'] - st['xyz_min']).prod() / num_voxels_base).pow(1 / 3)
+    st['voxel_size'] = ((st['xyz_max'] - st['xyz_min']).prod() / num_voxels).pow(1 / 3)
+    st['world_size'] = ((st['xyz_max'] - st['xyz_min']) / st['voxel_size']).long()
+    st['world_len'] = st['world_size'][0].item()
+    st['voxel_size_ratio'] = st['voxel_size'] / st['voxel_size_base']
+    st['act_shift'] = torch.FloatTensor([np.log(1 / (1 - alpha_init) - 1)])
+    ws = st['world_size'].tolist()
+    st['density'] = torch.zeros([1, 1, *ws])
+    st['rgbnet_dim'] = rgbnet_dim
+    if rgbnet_dim <= 0:
+        st['k0_dim'] = 3
+        st['rgbnet'] = None
+    else:
+        st['k0_dim'] = rgbnet_dim
+        st['viewfreq'] = torch.FloatTensor([(2 ** i) for i in range(viewbase_pe)])
+        dim0 = 3 + 3 * viewbase_pe * 2 + rgbnet_dim
+        st['dim0'] = dim0
+        dims = [dim0] + [rgbnet_width] * (rgbnet_depth - 1) + [3]
+        st['rgbnet'] = [(torch.zeros(dims[i + 1], dims[i]), torch.zeros(dims[i + 1])) for i in range(len(dims) - 1)]
+    st['k0'] = torch.zeros([1, st['k0_dim'], *ws])
+    if mask_cache_world_size is None:
+        mask_cache_world_size = ws
+    st['mask_cache'] = mask_grid_state(torch.ones(list(mask_cache_world_size), dtype=torch.bool), st['xyz_min'], st['xyz_max'])
+    return st
+
+
 def state_to(st, device):
     out = {}
     for k, v in st.items():
@@ -127,7 +164,7 @@ def state_to(st, device):
             out[k] = v.to(device)
         elif isinstance(v, dict):
             out[k] = state_to(v, device)
-        elif isinstance(v, list):
+        elif isinstance(v, list) and v and isinstance(v[0], tuple):
             out[k] = [tuple(t.to(device) for t in pair) for pair in v]
         else:
             out[k] = v
@@ -371,7 +408,80 @@ def dmpigo_forward(st, rays_o, rays_d, viewdirs, ops, stats=None, **render_kwarg
     return ret
 
 
+@torch.no_grad()
+def dcvgo_forward(st, rays_o, rays_d, viewdirs, ops, stats=None, **render_kwargs):
+    """DirectContractedVoxGO.forward (lib/dcvgo.py:264-382, sample_ray :226-262) at inference."""
+    dev = rays_o.device
+    N = len(rays_o)
+    stepsize = render_kwargs['stepsize']
+    # sample_ray
+    o = (rays_o - st['scene_center']) / st['scene_radius']
+    d = rays_d / rays_d.norm(dim=-1, keepdim=True)
+    N_inner = int(2 / (2 + 2 * st['bg_len']) * st['world_len'] / stepsize) + 1
+    N_outer = N_inner
+    b_inner = torch.linspace(0, 2, N_inner + 1, device=dev)
+    b_outer = 2 / torch.linspace(1, 1 / 128, N_outer + 1, device=dev)
+    t = torch.cat([(b_inner[1:] + b_inner[:-1]) * 0.5, (b_outer[1:] + b_outer[:-1]) * 0.5])
+    ray_pts = o[:, None, :] + d[:, None, :] * t[None, :, None]
+    norm = ray_pts.abs().amax(dim=-1, keepdim=True)
+    inner_mask = (norm <= 1)
+    ray_pts = torch.where(inner_mask, ray_pts, ray_pts / norm * ((1 + st['bg_len']) - st['bg_len'] / norm))
+    inner_mask = inner_mask.squeeze(-1)
+    n_max = len(t)
+    interval = float(stepsize * st['voxel_size_ratio'])
+    ray_id = torch.arange(N, device=dev).view(-1, 1).expand(N, n_max).flatten()
+    step_id = torch.arange(n_max, device=dev).view(1, -1).expand(N, n_max).flatten()
+    # skip oversampled points outside the scene bbox
+    mask = inner_mask.clone()
+    dist_thres = (2 + 2 * st['bg_len']) / st['world_len'] * stepsize * 0.95
+    dist = (ray_pts[:, 1:] - ray_pts[:, :-1]).norm(dim=-1)
+    mask[:, 1:] |= ops.cumdist_thres(dist.contiguous(), dist_thres)
+    ray_pts = ray_pts[mask]
+    tt = t[None].repeat(N, 1)[mask]
+    ray_id = ray_id[mask.flatten()]
+    step_id = step_id[mask.flatten()]
+    ids_m = (ray_id, step_id)
+
+    m1 = mask_grid(st['mask_cache'], ray_pts, ops)
+    ray_pts, tt, ray_id, step_id = ray_pts[m1], tt[m1], ray_id[m1], step_id[m1]
+    ids_d = (ray_id, step_id)
+
+    density = dense_grid(st['density'], ray_pts, st['xyz_min'], st['xyz_max'])
+    alpha = ops.raw2alpha(density.flatten().contiguous(), float(st['act_shift']), interval)[1].reshape(density.shape)
+    if st['fast_color_thres'] > 0:
+        m2 = (alpha > st['fast_color_thres'])
+        ray_pts, tt, ray_id, step_id, alpha = ray_pts[m2], tt[m2], ray_id[m2], step_id[m2], alpha[m2]
+    weights, _, alphainv_last, _, i_end = ops.alpha2weight(alpha.contiguous(), ray_id.contiguous(), N)
+    ray_stats = _early_out_counts(ids_m, ids_d, (ray_id, step_id), i_end, alphainv_last, N) if stats is not None else None
+    if st['fast_color_thres'] > 0:
+        m3 = (weights > st['fast_color_thres'])
+        ray_pts, tt, ray_id, step_id, alpha, weights = ray_pts[m3], tt[m3], ray_id[m3], step_id[m3], alpha[m3], weights[m3]
+    S_c = ray_pts.shape[0]
+
+    k0 = dense_grid(st['k0'], ray_pts, st['xyz_min'], st['xyz_max'])
+    if st['rgbnet'] is None:
+        rgb = torch.sigmoid(k0)
+    else:
+        viewdirs_emb = (viewdirs.unsqueeze(-1) * st['viewfreq']).flatten(-2)
+        viewdirs_emb = torch.cat([viewdirs, viewdirs_emb.sin(), viewdirs_emb.cos()], -1)
+        viewdirs_emb = viewdirs_emb.flatten(0, -2)[ray_id]
+        rgb = torch.sigmoid(mlp(st['rgbnet'], torch.cat([k0, viewdirs_emb], -1)))
+    rgb_marched = _segment_sum(weights.unsqueeze(-1) * rgb, ray_id, torch.zeros([N, 3], device=dev))
+    rgb_marched += (alphainv_last.unsqueeze(-1) * render_kwargs['bg'])
+    s = 1 - 1 / (1 + tt)
+    ret = {'alphainv_last': alphainv_last, 'weights': weights, 'rgb_marched': rgb_marched, 'rgb_feature': rgb_marched,
+           'raw_alpha': alpha, 'raw_rgb': rgb, 'ray_id': ray_id, 'step_id': step_id, 'n_max': n_max, 't': tt, 's': s}
+    if render_kwargs.get('render_depth', False):
+        ret['depth'] = _segment_sum(weights * s, ray_id, torch.zeros([N], device=dev))
+    if stats is not None:
+        _add_stats(stats, ids_m, ids_d, S_c, ray_stats, ray_id, N)
+        ret['_ray_stats'] = ray_stats
+    return ret
+
+
 def forward(st, rays_o, rays_d, viewdirs, ops, stats=None, **render_kwargs):
+    if st['kind'] == 'dcvgo':
+        return dcvgo_forward(st, rays_o, rays_d, viewdirs, ops, stats=stats, **render_kwargs)
     fn = dvgo_forward if st['kind'] == 'dvgo' else dmpigo_forward
     return fn(st, rays_o, rays_d, viewdirs, ops, stats=stats, **render_kwargs)
 

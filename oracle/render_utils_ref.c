@@ -236,6 +236,21 @@ K4O_API void k4o_alpha2weight(const float* alpha, const int64_t* ray_id, int64_t
     }
 }
 
+/* lib/cuda/ub360_utils_kernel.cu:12-32 cumdist_thres_cuda_kernel: per ray, accumulate the distances
+ * between consecutive samples; emit (and reset) whenever the sum exceeds thres. */
+K4O_API void k4o_cumdist_thres(const float* dist, float thres, int64_t n_rays, int64_t n_pts, uint8_t* mask) {
+#pragma omp parallel for schedule(static)
+    for (int64_t r = 0; r < n_rays; ++r) {
+        float cum = 0.f;
+        for (int64_t i = r * n_pts; i < (r + 1) * n_pts; ++i) {
+            cum += dist[i];
+            const int over = cum > thres;
+            cum *= (float)(!over);
+            mask[i] = (uint8_t)over;
+        }
+    }
+}
+
 /* ------------------------------------------------------------------------------------------
  * Counting helper used for the roofline figure: S_m, S_d, S_c are the
  * number of samples reaching the mask lookup / density fetch / feature fetch.  Pure bookkeeping

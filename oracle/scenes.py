@@ -117,6 +117,19 @@ def make_cfgB(xy=384, depth=256, regime='fog', width=64, k0_dim=9, viewbase_pe=0
     return st
 
 
+def make_cfgC(res=64, regime='fog', width=128, k0_dim=12, viewbase_pe=4, bg_len=0.2):
+    """Unbounded inward-facing scene: DirectContractedVoxGO (lib/dcvgo.py), fine-stage shape of
+    configs/default.py with the contracted background shell."""
+    st = pipeline.dcvgo_state([-1, -1, -1], [1, 1, 1], num_voxels=res ** 3, num_voxels_base=res ** 3,
+                              alpha_init=1e-2, fast_color_thres=1e-4, bg_len=bg_len, rgbnet_dim=k0_dim,
+                              rgbnet_depth=3, rgbnet_width=width, viewbase_pe=viewbase_pe)
+    st['kind'] = 'dvgo'          # fill_grids only distinguishes the MPI bias; contracted == bounded here
+    fill_grids(st, regime)
+    st['kind'] = 'dcvgo'
+    fill_rgbnet(st)
+    return st
+
+
 # ---------------------------------------------------------------------------------------------
 # cameras
 # ---------------------------------------------------------------------------------------------
@@ -175,5 +188,7 @@ def llff_rays(H, W, shift=(0.05, -0.03, 0.0), crop=None):
 
 RENDER_KW_DVGO = dict(near=2.0, far=6.0, bg=1, stepsize=0.5, inverse_y=False, flip_x=False, flip_y=False,
                       render_depth=True)
+RENDER_KW_DCVGO = dict(near=0.2, far=1e9, bg=1, stepsize=0.5, inverse_y=False, flip_x=False, flip_y=False,
+                       render_depth=True)
 RENDER_KW_MPI = dict(near=0, far=1, bg=0, stepsize=1.0, inverse_y=False, flip_x=False, flip_y=False,
                      render_depth=True)

@@ -19,6 +19,15 @@ def model_from_state(st, device=None):
                       viewbase_pe=len(st['viewfreq']))
         m = k4nerf.DirectVoxGO(**kw)
         del nvox
+    elif st['kind'] == 'dcvgo':
+        kw = dict(xyz_min=st['_fg_min'], xyz_max=st['_fg_max'], num_voxels=st['_num_voxels'],
+                  num_voxels_base=st['_num_voxels_base'], alpha_init=st['_alpha_init'],
+                  fast_color_thres=st['fast_color_thres'], bg_len=st['bg_len'], rgbnet_dim=st['rgbnet_dim'],
+                  mask_cache_world_size=list(st['mask_cache']['mask'].shape))
+        if st['rgbnet'] is not None:
+            kw.update(rgbnet_depth=len(st['rgbnet']), rgbnet_width=st['rgbnet'][0][0].shape[0],
+                      viewbase_pe=len(st['viewfreq']))
+        m = k4nerf.DirectContractedVoxGO(**kw)
     else:
         kw = dict(xyz_min=st['xyz_min'].tolist(), xyz_max=st['xyz_max'].tolist(),
                   num_voxels=st['_num_voxels'], mpi_depth=st['mpi_depth'],
@@ -56,6 +65,10 @@ def make_state(name, **kw):
         res = kw.pop('res', 48)
         st = scenes.make_cfgA(res=res, **kw)
         st.update(_num_voxels=res ** 3, _num_voxels_base=res ** 3, _alpha_init=1e-2)
+    elif name == 'cfgC':
+        res = kw.pop('res', 48)
+        st = scenes.make_cfgC(res=res, **kw)
+        st.update(_num_voxels=res ** 3, _num_voxels_base=res ** 3, _alpha_init=1e-2, _fg_min=[-1, -1, -1], _fg_max=[1, 1, 1])
     elif name == 'cfgB':
         xy, depth = kw.pop('xy', 48), kw.pop('depth', 32)
         st = scenes.make_cfgB(xy=xy, depth=depth, **kw)
@@ -66,6 +79,8 @@ def make_state(name, **kw):
 
 
 def rays_for(st, H, W, **kw):
+    if st['kind'] == 'dcvgo':
+        return scenes.blender_rays(H, W, **kw), dict(scenes.RENDER_KW_DCVGO)
     if st['kind'] == 'dvgo':
         return scenes.blender_rays(H, W, **kw), dict(scenes.RENDER_KW_DVGO)
     return scenes.llff_rays(H, W, **kw), dict(scenes.RENDER_KW_MPI)

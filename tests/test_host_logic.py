@@ -96,3 +96,30 @@ def test_sftnet_state_dict_matches_reference_names():
     assert len(n._ordered_convs()) == 229            # 229 convs per forward
     with pytest.raises(NotImplementedError):
         k4nerf.SFTNet(3, 2, 64, 5, 32, 1)
+
+
+def test_dcvgo_constructor_contract():
+    """DirectContractedVoxGO: buffers, derived sizes, checkpoint keys and the step list follow
+    lib/dcvgo.py:27-160,239-248."""
+    import numpy as np
+    m = k4nerf.DirectContractedVoxGO(xyz_min=[-2, -1, 0], xyz_max=[2, 3, 4], num_voxels=40 ** 3, num_voxels_base=40 ** 3,
+                                     alpha_init=1e-2, fast_color_thres=1e-4, bg_len=0.2, rgbnet_dim=12,
+                                     rgbnet_depth=3, rgbnet_width=128, viewbase_pe=4)
+    assert torch.equal(m.scene_center, torch.tensor([0., 1., 2.])) and torch.equal(m.scene_radius, torch.tensor([2., 2., 2.]))
+    assert torch.allclose(m.xyz_min, torch.tensor([-1.2] * 3)) and torch.allclose(m.xyz_max, torch.tensor([1.2] * 3))
+    assert m.world_len == int(m.world_size[0]) and list(m.density.grid.shape) == [1, 1] + m.world_size.tolist()
+    assert abs(float(m.act_shift) - np.log(1 / (1 - 1e-2) - 1)) < 1e-6
+    keys = set(m.state_dict().keys())
+    assert {'scene_center', 'scene_radius', 'xyz_min', 'xyz_max', 'act_shift', 'viewfreq', 'density.grid', 'k0.grid',
+            'mask_cache.mask', 'rgbnet.0.weight', 'rgbnet.2.0.weight', 'rgbnet.3.bias'} <= keys
+    assert m.rgbnet[0].in_features == 3 + 3 * 4 * 2 + 12
+    kw = m.get_kwargs()
+    assert kw['contracted_norm'] == 'inf' and kw['rgbnet_dim'] == 12 and kw['num_voxels'] == 40 ** 3
+    t = m.sample_t(0.5, 'cpu')
+    n_inner = int(2 / (2 + 2 * 0.2) * m.world_len / 0.5) + 1
+    assert t.numel() == 2 * n_inner and bool((t[1:] > t[:-1]).all())
+    assert abs(float(t[0]) - 1.0 / n_inner) < 1e-6 and float(t[-1]) > 100
+    assert m.resolve_mlp_mode('auto') == 'ws' and m.resolve_mlp_mode('tc') == 'ws' and m.resolve_mlp_mode('fp32') == 'fp32'
+    with pytest.raises(NotImplementedError):
+        k4nerf.DirectContractedVoxGO(xyz_min=[-1] * 3, xyz_max=[1] * 3, num_voxels=8 ** 3, num_voxels_base=8 ** 3,
+                                     alpha_init=1e-2, contracted_norm='l2')

@@ -104,3 +104,33 @@ def test_c_ops_against_double_precision_formulas():
     assert 0 < k < 40 and float(last[0]) < 1e-3 and float(T[k - 1]) >= 1e-3
     assert torch.all(w[k:] == 0) and torch.all(T[k:] == 1)
     assert abs(float(w.sum() + last[0]) - 1.0) < 1e-6
+
+
+def test_cumdist_thres_restatement():
+    """k4o_cumdist_thres vs a literal loop over lib/cuda/ub360_utils_kernel.cu:12-32."""
+    import numpy as np
+    g = torch.Generator().manual_seed(11)
+    dist = torch.rand(7, 29, generator=g) * 0.03
+    thres = 0.05
+    got = ops.CpuOps.cumdist_thres(dist, thres)
+    want = torch.zeros_like(got)
+    for r in range(dist.shape[0]):
+        cum = np.float32(0)
+        for i in range(dist.shape[1]):
+            cum = np.float32(cum + np.float32(dist[r, i].item()))
+            over = bool(cum > np.float32(thres))
+            want[r, i] = over
+            if over:
+                cum = np.float32(0)
+    assert torch.equal(got, want) and int(got.sum()) > 0
+
+
+def test_dcvgo_oracle_runs_and_is_deterministic():
+    from helpers import make_state, rays_for
+    st = make_state('cfgC', res=24, regime='shell')
+    (ro, rd, vd), kw = rays_for(st, 12, 16, radius=0.6)
+    s1, s2 = {}, {}
+    a = pipeline.forward(st, ro, rd, vd, ops.CpuOps, stats=s1, **kw)
+    b = pipeline.forward(st, ro, rd, vd, ops.CpuOps, stats=s2, **kw)
+    assert torch.equal(a['rgb_marched'], b['rgb_marched']) and s1 == s2
+    assert 0 < s1['S_c'] <= s1['S_d'] <= s1['S_m'] and a['depth'].min() >= 0 and a['depth'].max() <= 1

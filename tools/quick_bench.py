@@ -24,15 +24,18 @@ def main():
     ap.add_argument('--kind', default='cfgA')
     ap.add_argument('--iters', type=int, default=5)
     ap.add_argument('--linear', action='store_true')
+    ap.add_argument('--radius', type=float, default=0.0)
     a = ap.parse_args()
     dev = torch.device('cuda', 0)
     H, W = a.hw
     for regime in a.regimes:
         if a.kind == 'cfgA':
             st = make_state('cfgA', res=a.res, regime=regime)
+        elif a.kind == 'cfgC':
+            st = make_state('cfgC', res=a.res, regime=regime)
         else:
             st = make_state('cfgB', xy=384, depth=256, regime=regime)
-        (ro, rd, vd), kw = rays_for(st, H, W)
+        (ro, rd, vd), kw = rays_for(st, H, W, **({'radius': a.radius} if a.radius else {}))
         m = model_from_state(st, dev)
         ro, rd, vd = ro.to(dev), rd.to(dev), vd.to(dev)
         for mode in a.modes:
