@@ -128,3 +128,83 @@ def render_frame_sharded(render_fn, rays_o, rays_d, viewdirs, H, W, group=None, 
     gathered = torch.empty(world * 5 * n_pad, device=buf.device, dtype=torch.float32)
     dist.all_gather_into_tensor(gathered, buf, group=group)
     return unpack_frame(gathered, H, W, world)
+
+
+# ------------------------------------------------------------------------------------------------
+# VC-Decoder sharding: by reference tile, tiles split into row parts with a
+# recomputed halo when there are more ranks than tiles.
+# ------------------------------------------------------------------------------------------------
+def sr_units(height, width, tile_size, tile_pad, world_size, halo):
+    """Work units of one x4 decode.  The reference's tile geometry (lib/sr_esrnet.py:467-527) is part
+    of the result (the 10-pixel pad is far smaller than the receptive field), so the units are the
+    reference tiles; with more ranks than tiles every tile's OUTPUT rows are cut into
+    ``ceil(world/tiles)`` parts, each computed from its rows plus ``halo`` rows above and below,
+    clipped to the PADDED TILE (beyond it the un-split tile sees zero padding too).  With ``halo`` >=
+    the network's receptive radius every part reproduces the un-split tile's pixels exactly.
+
+    Returns a list of dicts: ``src`` = (y0, y1, x0, x1) input crop in LR pixels, ``keep`` = (ky, kx)
+    offset of the kept block inside the unit's output in LR pixels, ``dst`` = (y0, y1, x0, x1) LR
+    rect of the kept block in the image."""
+    import math
+    tiles_x = math.ceil(width / tile_size)
+    tiles_y = math.ceil(height / tile_size)
+    n_tiles = tiles_x * tiles_y
+    n_split = max(1, math.ceil(world_size / n_tiles))
+    units = []
+    for ty in range(tiles_y):
+        for tx in range(tiles_x):
+            x0, y0 = tx * tile_size, ty * tile_size
+            x1, y1 = min(x0 + tile_size, width), min(y0 + tile_size, height)
+            x0p, x1p = max(x0 - tile_pad, 0), min(x1 + tile_pad, width)
+            y0p, y1p = max(y0 - tile_pad, 0), min(y1 + tile_pad, height)
+            rows = y1 - y0
+            for k in range(n_split):
+                ya = y0 + (rows * k) // n_split
+                yb = y0 + (rows * (k + 1)) // n_split
+                if yb <= ya:
+                    continue
+                sa = y0p if k == 0 else max(ya - halo, y0p)
+                sb = y1p if k == n_split - 1 else min(yb + halo, y1p)
+                units.append({'src': (sa, sb, x0p, x1p), 'keep': (ya - sa, x0 - x0p), 'dst': (ya, yb, x0, x1)})
+    return units
+
+
+def sr_decode_sharded(net_fn, img, cond, tile_size, tile_pad=10, scale=4, halo=80, group=None):
+    """x`scale` decode of ``img [1,C,H,W]`` / ``cond [1,H,W]`` (full frame on every rank) with the units
+    of :func:`sr_units` dealt round-robin over the ranks and ONE all-gather of the packed output
+    blocks.  ``net_fn(img_crop, cond_crop[1,1,h,w]) -> [1,C,scale*h,scale*w]`` is the decoder
+    (``SFTNet.forward``).  Every rank returns the full ``[1,C,scale*H,scale*W]`` frame."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    _, C, H, W = img.shape
+    s = scale
+    units = sr_units(H, W, tile_size, tile_pad, world, halo)
+    size = lambda u: C * (u['dst'][1] - u['dst'][0]) * (u['dst'][3] - u['dst'][2]) * s * s
+    per_rank = [sum(size(u) for u in units[r::world]) for r in range(world)]
+    n_pad = max(per_rank) if per_rank else 0
+    buf = torch.zeros(n_pad, device=img.device, dtype=img.dtype)
+    off = 0
+    cond4 = cond.unsqueeze(0)
+    for u in units[rank::world]:
+        sa, sb, xa, xb = u['src']
+        out = net_fn(img[:, :, sa:sb, xa:xb], cond4[:, :, sa:sb, xa:xb])
+        ky, kx = u['keep']
+        y0, y1, x0, x1 = u['dst']
+        blk = out[0, :, ky * s:(ky + y1 - y0) * s, kx * s:(kx + x1 - x0) * s]
+        buf[off:off + blk.numel()] = blk.reshape(-1)
+        off += blk.numel()
+    if world > 1:
+        gathered = torch.empty(world * n_pad, device=img.device, dtype=img.dtype)
+        dist.all_gather_into_tensor(gathered, buf, group=group)
+    else:
+        gathered = buf
+    g = gathered.view(world, n_pad)
+    output = img.new_zeros((1, C, H * s, W * s))
+    for r in range(world):
+        off = 0
+        for u in units[r::world]:
+            y0, y1, x0, x1 = u['dst']
+            n = size(u)
+            output[0, :, y0 * s:y1 * s, x0 * s:x1 * s] = g[r, off:off + n].view(C, (y1 - y0) * s, (x1 - x0) * s)
+            off += n
+    return output

@@ -127,3 +127,28 @@ def render_frame_4k(model, net_sr, H, W, K, c2w, ndc, render_kwargs, test_tile=5
     if out_u8:
         sr = (sr * 255).to(torch.uint8).permute(1, 2, 0).contiguous()     # to8b: (255*clip(x,0,1)).astype(uint8)
     return sr, lr
+
+
+@torch.no_grad()
+def render_frame_4k_sharded(model, net_sr, H, W, K, c2w, ndc, render_kwargs, test_tile=510, out_u8=False,
+                            flip_x=False, flip_y=False, group=None):
+    """:func:`render_frame_4k` across the ranks of ``group`` (one process per GPU, scene and decoder
+    replicated): every rank marches its 8-row blocks of the LR frame
+    (one all-gather of the packed ``[rgb|depth|alphainv]`` rows), then decodes its share of the
+    reference tiles / tile row-parts (one all-gather of the x4 blocks).  Every rank returns the full
+    frame; values are identical to the single-GPU :func:`render_frame_4k`."""
+    from . import dist as kdist
+    rays_o, rays_d, viewdirs = dvgo.get_rays_of_a_view(
+        H, W, K, torch.as_tensor(np.asarray(c2w), dtype=torch.float32), ndc,
+        inverse_y=render_kwargs['inverse_y'], flip_x=flip_x, flip_y=flip_y)
+    kw = dict(render_kwargs)
+    kw['render_depth'] = True
+    fn = lambda ro, rd, vd, hw: model.render_rays(ro.contiguous(), rd.contiguous(), vd.contiguous(), kw, image_hw=hw)
+    lr = kdist.render_frame_sharded(fn, rays_o.view(-1, 3), rays_d.view(-1, 3), viewdirs.view(-1, 3), H, W, group=group)
+    x = lr['rgb_marched'].view(H, W, 3).permute(2, 0, 1).unsqueeze(0).contiguous()
+    cond = lr['depth'].view(1, H, W).contiguous()
+    sr = net_sr.tile_process_sharded(x, cond, tile_size=test_tile if test_tile else max(H, W), group=group)
+    sr = sr.squeeze(0).clamp_(0, 1)
+    if out_u8:
+        sr = (sr * 255).to(torch.uint8).permute(1, 2, 0).contiguous()
+    return sr, lr

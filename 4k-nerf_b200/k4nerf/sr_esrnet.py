@@ -165,6 +165,22 @@ class SFTNet(nn.Module):
                 output[:, :, y0 * s:y1 * s, x0 * s:x1 * s] = out_tile[:, :, ty:ty + (y1 - y0) * s, tx:tx + (x1 - x0) * s]
         return output.to('cpu') if to_cpu else output
 
+    def receptive_halo(self):
+        """LR rows a decoded pixel can depend on above/below it: conv_first/CondNet.0 (1) + 15 3x3 convs
+        per RRDB_SFT + conv_body (1) + the four 3x3 convs after the nearest upsamplings (1/2 + 3/4 LR
+        pixels), rounded up to an even count.  Row parts of a tile cut with this halo reproduce the
+        un-split tile exactly (dist.sr_units)."""
+        r = 1 + 15 * len(self.body) + 1 + 2
+        return r + (r & 1)
+
+    def tile_process_sharded(self, img, cond, tile_size, tile_pad=10, group=None):
+        """tile_process across the ranks of ``group``: reference tiles (split into
+        row parts with a recomputed halo when ranks outnumber tiles) dealt round-robin, one all-gather;
+        every rank returns the same full frame as single-GPU ``tile_process`` (device resident)."""
+        from . import dist as kdist
+        return kdist.sr_decode_sharded(lambda x, c: self(x, c), img, cond, tile_size, tile_pad, self.scale,
+                                       self.receptive_halo(), group)
+
     def load_network(self, load_path, device, strict=True, param_key='params_ema'):
         """lib/sr_esrnet.py:529-554 (keys may carry a 'module.' prefix; mismatching sizes are skipped
         when strict=False)."""

@@ -354,6 +354,8 @@ def main():
     extra = {}
     if not args.no_extra and world == 1:
         extra = secondary(model, st, model_from_state, kw, dev, mode, args)
+    elif not args.no_extra:
+        extra = secondary_sharded(model, kw, dev, world)
 
     if rank == 0:
         peak, peak_src = hbm_peak()
@@ -478,6 +480,42 @@ def secondary(model, st, model_from_state, kw, dev, mode, args):
             'full_4k_nerf_frame_ms (march 1008x756 ' + args.regime + ' + decode)': lr + ms_sr}
     except Exception as e:
         out['configs[3]_error'] = repr(e)
+    return out
+
+
+def secondary_sharded(model, kw, dev, world):
+    """configs[4] (N>1): the whole 4K-NeRF frame across the ranks -- 1008x756 marcher (8-row blocks,
+    one all-gather) + VC-Decoder x4 sharded by reference tile / tile row-parts (one all-gather).
+    Device timed, max over ranks."""
+    import k4nerf
+    from k4nerf import render as krender
+    from k4nerf import dist as krender_dist
+    from oracle import scenes, sftnet
+    out = {}
+    try:
+        net = k4nerf.SFTNet(3, 4, 64, 5, 32, 1)
+        net.load_state_dict(sftnet.random_state_dict(seed=3, scale=1.0))
+        net = net.to(dev)
+        K, c2w = scenes.blender_camera(HLR, WLR, *POSES[0])
+        run = lambda: krender.render_frame_4k_sharded(model, net, HLR, WLR, K, c2w, False, kw, test_tile=510)
+        for _ in range(2):
+            run()
+        torch.cuda.synchronize()
+        dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3):
+            sr, _ = run()
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / 3], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        out['configs[4]_full_frame_1008x756_to_4032x3024_sharded'] = {
+            'ms_per_frame': t.item(), 'frames_per_s': 1e3 / t.item(), 'n_gpus': world,
+            'decoder_units': len(krender_dist.sr_units(HLR, WLR, 510, 10, world, net.receptive_halo())),
+            'sr_mean': float(sr.mean())}
+    except Exception as e:
+        out['configs[4]_error'] = repr(e)
     return out
 
 

@@ -74,3 +74,93 @@ def test_band_arithmetic():
             cyc = sorted(int(x) for r in range(world) for x in kdist.cyclic_rows(H, r, world))
             assert cyc == list(range(H))
             assert all(kdist.cyclic_rows(H, r, world).numel() <= kdist.cyclic_pad_rows(H, world) for r in range(world))
+
+
+# ---------------------------------------------------------------------------------------------
+# decoder sharding (k4nerf.dist.sr_units / sr_decode_sharded)
+# ---------------------------------------------------------------------------------------------
+def _fake_decoder(x, c):
+    """Stand-in x4 'decoder' with a 2-pixel receptive radius and zero padding (5x5 box filter of
+    img + cond, then nearest x4): tiling, halo and zero-padding behaviour are all exercised."""
+    import torch.nn.functional as F
+    y = x + c
+    k = torch.ones(3, 1, 5, 5, dtype=x.dtype) / 25
+    y = F.conv2d(y, k, padding=2, groups=3)
+    return F.interpolate(y, scale_factor=4, mode='nearest')
+
+
+def _tile_process_local(fn, img, cond, tile, pad):
+    import math
+    _, C, H, W = img.shape
+    out = img.new_zeros((1, C, 4 * H, 4 * W))
+    c4 = cond.unsqueeze(0)
+    for ty in range(math.ceil(H / tile)):
+        for tx in range(math.ceil(W / tile)):
+            x0, y0 = tx * tile, ty * tile
+            x1, y1 = min(x0 + tile, W), min(y0 + tile, H)
+            x0p, x1p, y0p, y1p = max(x0 - pad, 0), min(x1 + pad, W), max(y0 - pad, 0), min(y1 + pad, H)
+            o = fn(img[:, :, y0p:y1p, x0p:x1p], c4[:, :, y0p:y1p, x0p:x1p])
+            out[:, :, 4 * y0:4 * y1, 4 * x0:4 * x1] = o[:, :, 4 * (y0 - y0p):4 * (y0 - y0p + y1 - y0), 4 * (x0 - x0p):4 * (x0 - x0p + x1 - x0)]
+    return out
+
+
+def _sr_worker(rank, world, port, H, W, tile, q):
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, '4k-nerf_b200'))
+    from k4nerf import dist as kdist
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    g = torch.Generator().manual_seed(9)
+    img = torch.randn(1, 3, H, W, generator=g)
+    cond = torch.randn(1, H, W, generator=g)
+    ref = _tile_process_local(_fake_decoder, img, cond, tile, 1)
+    full = kdist.sr_decode_sharded(_fake_decoder, img, cond, tile, tile_pad=1, scale=4, halo=2)
+    q.put((rank, bool(torch.equal(full, ref))))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('H,W,tile', [(23, 31, 16), (40, 12, 64)])
+def test_decoder_sharding_world2_gloo(H, W, tile):
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_sr_worker, args=(r, 2, port, H, W, tile, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(ok for _, ok in res), res
+
+
+def test_sr_units_cover_and_halo():
+    """Units tile the frame exactly once for every world size; splitting a tile into row parts with
+    halo >= receptive radius reproduces the un-split tile (single process, simulated ranks)."""
+    from k4nerf import dist as kdist
+    for (H, W, tile) in ((756, 1008, 510), (100, 70, 510), (33, 65, 32)):
+        for world in (1, 2, 3, 4, 8, 16):
+            units = kdist.sr_units(H, W, tile, 10, world, 80)
+            cover = torch.zeros(H, W, dtype=torch.int32)
+            for u in units:
+                y0, y1, x0, x1 = u['dst']
+                cover[y0:y1, x0:x1] += 1
+                sa, sb, xa, xb = u['src']
+                assert 0 <= sa <= y0 and y1 <= sb <= H and 0 <= xa <= x0 and x1 <= xb <= W
+                assert u['keep'] == (y0 - sa, x0 - xa)
+            assert bool((cover == 1).all()), (H, W, tile, world)
+            assert len(units) >= min(world, len(kdist.sr_units(H, W, tile, 10, 1, 80)))
+    g = torch.Generator().manual_seed(2)
+    img, cond = torch.randn(1, 3, 41, 37, generator=g), torch.randn(1, 41, 37, generator=g)
+    ref = _tile_process_local(_fake_decoder, img, cond, 24, 1)
+    for world in (1, 3, 8):
+        units = kdist.sr_units(41, 37, 24, 1, world, 2)
+        out = torch.zeros_like(ref)
+        for u in units:
+            sa, sb, xa, xb = u['src']
+            o = _fake_decoder(img[:, :, sa:sb, xa:xb], cond.unsqueeze(0)[:, :, sa:sb, xa:xb])
+            ky, kx = u['keep']
+            y0, y1, x0, x1 = u['dst']
+            out[:, :, 4 * y0:4 * y1, 4 * x0:4 * x1] = o[:, :, 4 * ky:4 * (ky + y1 - y0), 4 * kx:4 * (kx + x1 - x0)]
+        assert torch.equal(out, ref), world

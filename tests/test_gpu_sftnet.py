@@ -73,3 +73,31 @@ def test_parameter_update_rebuilds_device_copy(net, cuda_device):
     assert abs((b - a).mean().item() - 0.25) < 1e-3
     with torch.no_grad():
         net.conv_last.bias.sub_(0.25)
+
+
+@pytest.mark.parametrize('world', [2, 3])
+def test_row_parts_with_halo_reproduce_the_unsplit_tile(net, cuda_device, world):
+    """Multi-GPU decoder sharding (k4nerf.dist.sr_units): a tile cut into row parts with
+    SFTNet.receptive_halo() rows of recomputed halo gives bit-identical pixels to the un-split
+    tile (simulated ranks on one GPU: same units, run one after another)."""
+    from k4nerf import dist as kdist
+    assert net.receptive_halo() == 80
+    g = torch.Generator().manual_seed(21)
+    H, W = 300, 40
+    x = (torch.rand(1, 3, H, W, generator=g) * 1.2 - 0.1).to(cuda_device)
+    c = torch.rand(1, H, W, generator=g).to(cuda_device)
+    ref = net.tile_process(x, c, tile_size=510, tile_pad=10, to_cpu=False)
+    units = kdist.sr_units(H, W, 510, 10, world, net.receptive_halo())
+    assert len(units) == world
+    out = torch.zeros_like(ref)
+    for u in units:
+        sa, sb, xa, xb = u['src']
+        assert sb - sa < H                       # really a part, with a non-clipped halo on one side at least
+        o = net(x[:, :, sa:sb, xa:xb], c.unsqueeze(0)[:, :, sa:sb, xa:xb])
+        ky, kx = u['keep']
+        y0, y1, x0, x1 = u['dst']
+        out[:, :, 4 * y0:4 * y1, 4 * x0:4 * x1] = o[:, :, 4 * ky:4 * (ky + y1 - y0), 4 * kx:4 * (kx + x1 - x0)]
+    assert torch.equal(out, ref), (out - ref).abs().max().item()
+    # and through the collective-free single-process path of the sharded driver
+    full = net.tile_process_sharded(x, c, tile_size=510, tile_pad=10)
+    assert torch.equal(full, ref)

@@ -1,0 +1,70 @@
+"""torchrun check (N GPUs of one node): the sharded full-frame driver returns, on every rank, exactly
+the frame the single-GPU driver returns.  torchrun --nproc-per-node N tools/frame_sharded_check.py"""
+import json
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, '4k-nerf_b200'))
+sys.path.insert(0, os.path.join(ROOT, 'tests'))
+
+import k4nerf  # noqa: E402
+from k4nerf import render as krender  # noqa: E402
+from helpers import make_state, model_from_state  # noqa: E402
+from oracle import scenes, sftnet  # noqa: E402
+
+
+def main():
+    rank, world = int(os.environ.get('RANK', 0)), int(os.environ.get('WORLD_SIZE', 1))
+    dev = torch.device('cuda', int(os.environ.get('LOCAL_RANK', 0)))
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    H, W = 756, 1008
+    res = {}
+    for regime in ('shell', 'fog'):
+        st = make_state('cfgA', res=160, regime=regime)
+        model = model_from_state(st, dev)
+        net = k4nerf.SFTNet(3, 4, 64, 5, 32, 1)
+        net.load_state_dict(sftnet.random_state_dict(seed=3, scale=1.0))
+        net = net.to(dev)
+        kw = dict(scenes.RENDER_KW_DVGO)
+        K, c2w = scenes.blender_camera(H, W)
+        model.mlp_mode = 'f16x3'          # deterministic accumulation order per ray (the ws kernel's atomics are not)
+        ref, lr_ref = krender.render_frame_4k(model, net, H, W, K, c2w, False, kw, test_tile=510)
+        sr, lr = krender.render_frame_4k_sharded(model, net, H, W, K, c2w, False, kw, test_tile=510)
+        same_lr = all(torch.equal(lr[k], lr_ref[k]) for k in ('rgb_marched', 'depth', 'alphainv_last'))
+        same = bool(torch.equal(sr, ref))
+        t = torch.tensor([int(same), int(same_lr)], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        res[regime] = {'sr_identical_all_ranks': bool(t[0].item()), 'lr_identical_all_ranks': bool(t[1].item()),
+                       'maxabs': (sr - ref).abs().max().item()}
+        model.mlp_mode = 'auto'
+        for _ in range(2):
+            krender.render_frame_4k_sharded(model, net, H, W, K, c2w, False, kw, test_tile=510)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            krender.render_frame_4k_sharded(model, net, H, W, K, c2w, False, kw, test_tile=510)
+        e1.record()
+        torch.cuda.synchronize()
+        tm = torch.tensor([e0.elapsed_time(e1) / 5], device=dev)
+        if world > 1:
+            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        res[regime]['ms_per_frame'] = tm.item()
+    if rank == 0:
+        print(json.dumps({'n_gpus': world, 'frame': '1008x756 -> 4032x3024', **res}), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()
