@@ -223,10 +223,13 @@ class FusedRenderMixin:
         reference aliases it and adds the background in place, lib/dvgo.py:425-427) and ``depth [N]``
         when ``render_kwargs['render_depth']``.  The flat per-sample lists the reference also returns
         (``weights``, ``raw_alpha``, ``raw_rgb``, ``ray_id``, ``s``) are training-only and are never
-        materialised by the fused kernel ("next").
+        materialised by the fused kernel; with autograd enabled (training) the call is routed to
+        ``train_forward.forward_samples``, which returns them.
         """
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()) and global_step is not None:
-            raise NotImplementedError('k4nerf renders at inference only; training (autograd) is out of scope')
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            # training: the materialised, differentiable pipeline on the op-level kernels (section 8 f-2)
+            from .train_forward import forward_samples
+            return forward_samples(self, rays_o, rays_d, viewdirs, global_step=global_step, **render_kwargs)
         ret = self.render_rays(rays_o, rays_d, viewdirs, render_kwargs)
         ret['rgb_feature'] = ret['rgb_marched']
         return ret

@@ -8,9 +8,10 @@ import torch.nn as nn
 
 from . import _lib, grid
 from ._scene import FusedRenderMixin
+from .maintain import GridMaintenanceMixin
 
 
-class DirectContractedVoxGO(FusedRenderMixin, nn.Module):
+class DirectContractedVoxGO(FusedRenderMixin, GridMaintenanceMixin, nn.Module):
     _k4_kind = _lib.K4_KIND_DCVGO
 
     def __init__(self, xyz_min, xyz_max,

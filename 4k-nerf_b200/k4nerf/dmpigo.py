@@ -6,9 +6,10 @@ import torch.nn as nn
 
 from . import _lib, grid
 from ._scene import FusedRenderMixin
+from .maintain import GridMaintenanceMixin
 
 
-class DirectMPIGO(FusedRenderMixin, nn.Module):
+class DirectMPIGO(FusedRenderMixin, GridMaintenanceMixin, nn.Module):
     _k4_kind = _lib.K4_KIND_DMPIGO
 
     def __init__(self, xyz_min, xyz_max,
@@ -90,6 +91,17 @@ class DirectMPIGO(FusedRenderMixin, nn.Module):
         self.world_size[:2] = (self.xyz_max - self.xyz_min)[:2] * r
         self.world_size[2] = self.mpi_depth
         self.voxel_size_ratio = 256. / mpi_depth
+
+    # ---- grid maintenance (maintain.py) specifics of the MPI model ----
+    _k4_shift_in_alpha = False          # activate_density: Raw2Alpha(density, 0, interval), lib/dmpigo.py:258-261
+
+    def _rescaled_density_for_mask(self):
+        return self.density.get_dense_grid() + self.act_shift.grid           # lib/dmpigo.py:205
+
+    def _tv_weights(self, weight):
+        wxy = weight * self.world_size[:2].max() / 128                       # lib/dmpigo.py:247-255
+        wz = weight * self.mpi_depth / 128
+        return wxy, wxy, wz
 
     def get_kwargs(self):
         return {

@@ -6,9 +6,10 @@ import torch.nn as nn
 
 from . import _lib, grid
 from ._scene import FusedRenderMixin
+from .maintain import GridMaintenanceMixin
 
 
-class DirectVoxGO(FusedRenderMixin, nn.Module):
+class DirectVoxGO(FusedRenderMixin, GridMaintenanceMixin, nn.Module):
     _k4_kind = _lib.K4_KIND_DVGO
 
     def __init__(self, xyz_min, xyz_max,

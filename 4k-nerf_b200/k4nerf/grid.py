@@ -1,9 +1,10 @@
 """Parameter holders with the reference's module tree and state-dict keys (lib/grid.py).
 
-The reference's DenseGrid.forward / MaskGrid.forward (lib/grid.py:117-128,295-304) are not
-reimplemented as separate ops: interpolation and occupancy lookup happen inside the fused marcher
-(csrc/k4_march.cu).  These classes only own the tensors so that reference checkpoints load
-unchanged: ``density.grid``, ``density.xyz_min``, ``density.xyz_max``, ``mask_cache.mask``,
+At inference the reference's DenseGrid.forward / MaskGrid.forward (lib/grid.py:117-128,295-304)
+never run as separate ops: interpolation and occupancy lookup happen inside the fused marcher
+(csrc/k4_march.cu).  The ``forward`` methods here exist for the training-side callers (grid
+maintenance, the op-level training forward); the classes own the tensors so that reference
+checkpoints load unchanged: ``density.grid``, ``density.xyz_min``, ``density.xyz_max``, ``mask_cache.mask``,
 ``mask_cache.xyz2ijk_scale``, ``mask_cache.xyz2ijk_shift``.
 """
 import torch
@@ -26,6 +27,39 @@ class DenseGrid(nn.Module):
         self.register_buffer('xyz_max', torch.as_tensor(xyz_max, dtype=torch.float32).clone())
         self.grid = nn.Parameter(torch.zeros([1, channels, *[int(w) for w in world_size]]))
 
+    def forward(self, xyz):
+        """Trilinear lookup with autograd (lib/grid.py:117-128) -- ATen grid_sample; training side only."""
+        import torch.nn.functional as F
+        shape = xyz.shape[:-1]
+        xyz = xyz.reshape(1, 1, 1, -1, 3)
+        ind_norm = ((xyz - self.xyz_min) / (self.xyz_max - self.xyz_min)).flip((-1,)) * 2 - 1
+        out = F.grid_sample(self.grid, ind_norm, mode='bilinear', align_corners=True)
+        out = out.reshape(self.channels, -1).T.reshape(*shape, self.channels)
+        return out.squeeze(-1) if self.channels == 1 else out
+
+    @torch.no_grad()
+    def scale_volume_grid(self, new_world_size):
+        """lib/grid.py:130-135: trilinear resample (align_corners=True) to the new resolution, one launch
+        of csrc/k4_train.cu for all channels."""
+        from . import _lib
+        from .render_utils_cuda import _p, _s, _call
+        ws = [int(w) for w in new_world_size]
+        self.world_size = new_world_size
+        if self.channels == 0:
+            self.grid = nn.Parameter(torch.zeros([1, 0, *ws], device=self.grid.device))
+            return
+        src = self.grid.data.contiguous()
+        dst = torch.empty([1, self.channels, *ws], device=src.device, dtype=torch.float32)
+        _call('k4_op_resample_trilinear', _p(src), self.channels, int(src.shape[2]), int(src.shape[3]), int(src.shape[4]),
+              _p(dst), ws[0], ws[1], ws[2], _s(src))
+        self.grid = nn.Parameter(dst)
+        del _lib
+
+    def total_variation_add_grad(self, wx, wy, wz, dense_mode):
+        """Add the total-variation gradient to ``grid.grad`` in place (lib/grid.py:137-140)."""
+        from . import total_variation_cuda
+        total_variation_cuda.total_variation_add_grad(self.grid, self.grid.grad, float(wx), float(wy), float(wz), dense_mode)
+
     def get_dense_grid(self):
         return self.grid
 
@@ -47,3 +81,11 @@ class MaskGrid(nn.Module):
         xyz_len = xyz_max - xyz_min
         self.register_buffer('xyz2ijk_scale', (torch.Tensor(list(mask.shape)) - 1) / xyz_len)
         self.register_buffer('xyz2ijk_shift', -xyz_min * self.xyz2ijk_scale)
+
+    @torch.no_grad()
+    def forward(self, xyz):
+        """Nearest-voxel occupancy of world points (lib/grid.py:295-304)."""
+        from . import render_utils_cuda
+        shape = xyz.shape[:-1]
+        xyz = xyz.reshape(-1, 3).contiguous()
+        return render_utils_cuda.maskcache_lookup(self.mask, xyz, self.xyz2ijk_scale, self.xyz2ijk_shift).reshape(shape)

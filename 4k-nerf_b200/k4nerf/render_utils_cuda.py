@@ -158,3 +158,13 @@ def alpha2weight_backward(alpha, weight, T, alphainv_last, i_start, i_end, n_ray
         _call('k4_op_alpha2weight_backward', _p(alpha), _p(weight), _p(T), _p(alphainv_last), _p(i_start), _p(i_end), int(n_rays),
               _p(grad_weights), _p(grad_last), _p(grad), _s(alpha))
     return grad
+
+
+def cumdist_thres(dist, thres):
+    """``ub360_utils_cuda.cumdist_thres`` (lib/cuda/ub360_utils.cpp:20-22), the one function of the
+    reference's second sampling extension: dist [n_rays, n_pts] -> bool mask of the kept samples."""
+    _chk(dist)
+    mask = torch.zeros(dist.shape, dtype=torch.bool, device=dist.device)
+    if dist.numel():
+        _call('k4_op_cumdist_thres', _p(dist), float(thres), dist.shape[0], dist.shape[1], _p(mask), _s(dist))
+    return mask

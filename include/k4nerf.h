@@ -241,6 +241,36 @@ K4_API int k4_op_alpha2weight_backward(const float* d_alpha, const float* d_weig
                                        const int64_t* d_i_start, const int64_t* d_i_end, int64_t n_rays,
                                        const float* d_grad_weights, const float* d_grad_last, float* d_grad, k4_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Grid maintenance and optimiser steps either side of the render path during training
+ * (SURVEY.md section 8 f-4).  Device pointers unless prefixed h_; caller's stream; no host sync.
+ *   reference                                                       entry point
+ *   total_variation_cuda.total_variation_add_grad (lib/cuda/total_variation.cpp:16-20; param
+ *       [1,C,I,J,K] contiguous, grad updated in place; !dense_mode skips grad==0)   k4_op_total_variation_add_grad
+ *   adam_upd_cuda.adam_upd / masked_adam_upd / adam_upd_with_perlr (lib/cuda/adam_upd.cpp:37-75;
+ *       d_perlr != NULL selects the per-voxel-lr variant, else skip_zero_grad the masked one;
+ *       `step` is the 1-based step count after the increment, lib/masked_adam.py:57)  k4_op_adam_upd
+ *   update_occupancy_cache (lib/dvgo.py:224-233, lib/dmpigo.py:212-224): alpha of the trilinear density
+ *       at the occupancy grid's points (d_lx/ly/lz = the three torch.linspace vectors), then
+ *       mask &= max_pool3d(alpha, 3, stride 1, pad 1) > thres              k4_op_grid_alpha, k4_op_maxpool3_thres_and
+ *   DenseGrid.scale_volume_grid (lib/grid.py:130-135: F.interpolate(mode='trilinear',
+ *       align_corners=True) of a [1,C,X,Y,Z] grid to [1,C,X2,Y2,Z2])        k4_op_resample_trilinear
+ */
+K4_API int k4_op_total_variation_add_grad(const float* d_param, float* d_grad, float wx, float wy, float wz, int32_t dense_mode,
+                                          int64_t n, int32_t sz_i, int32_t sz_j, int32_t sz_k, k4_stream_t stream);
+K4_API int k4_op_adam_upd(float* d_param, const float* d_grad, float* d_exp_avg, float* d_exp_avg_sq, const float* d_perlr,
+                          int64_t n, int32_t step, float beta1, float beta2, float lr, float eps, int32_t skip_zero_grad,
+                          k4_stream_t stream);
+K4_API int k4_op_grid_alpha(const float* d_density, int32_t X, int32_t Y, int32_t Z, const float* h_xyz_min, const float* h_xyz_max,
+                            const float* d_lx, const float* d_ly, const float* d_lz, int32_t mX, int32_t mY, int32_t mZ,
+                            float shift, float interval, float* d_alpha, k4_stream_t stream);
+K4_API int k4_op_maxpool3_thres_and(const float* d_alpha, int32_t mX, int32_t mY, int32_t mZ, float thres, uint8_t* d_mask,
+                                    k4_stream_t stream);
+/* ub360_utils_cuda.cumdist_thres (lib/cuda/ub360_utils.cpp:20-22; dist [n_rays, n_pts] -> bool mask, bit-identical) */
+K4_API int k4_op_cumdist_thres(const float* d_dist, float thres, int64_t n_rays, int64_t n_pts, uint8_t* d_mask, k4_stream_t stream);
+K4_API int k4_op_resample_trilinear(const float* d_src, int32_t C, int32_t X, int32_t Y, int32_t Z, float* d_dst, int32_t X2,
+                                    int32_t Y2, int32_t Z2, k4_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

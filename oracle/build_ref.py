@@ -38,6 +38,9 @@ OUT_UB360 = os.path.join(OUT_DIR, 'ub360_utils_cuda.so')      # cumdist_thres of
 MODULES = {
     'render_utils_cuda': (('render_utils.cpp', 'render_utils_kernel.cu'), OUT_SO),
     'ub360_utils_cuda': (('ub360_utils.cpp', 'ub360_utils_kernel.cu'), OUT_UB360),
+    # grid-maintenance steps either side of the path during training
+    'total_variation_cuda': (('total_variation.cpp', 'total_variation_kernel.cu'), os.path.join(OUT_DIR, 'total_variation_cuda.so')),
+    'adam_upd_cuda': (('adam_upd.cpp', 'adam_upd_kernel.cu'), os.path.join(OUT_DIR, 'adam_upd_cuda.so')),
 }
 
 

@@ -55,7 +55,8 @@ def test_dcvgo_fused_vs_cpu_oracle(cuda_device, regime, radius):
     for mode, bar in (('fp32', 80.0), ('f16x3', 70.0), ('f16', 70.0), ('ws', 70.0), ('auto', 70.0)):
         ours = m.render_rays(ro.to(dev), rd.to(dev), vd.to(dev), kw, image_hw=(48, 64), mlp_mode=mode, debug=True)
         _check(ours, ref, stats, ro.shape[0], mode, bar)
-    out = m(ro.to(dev), rd.to(dev), vd.to(dev), **kw)
+    with torch.no_grad():
+        out = m(ro.to(dev), rd.to(dev), vd.to(dev), **kw)
     assert out['rgb_feature'] is out['rgb_marched'] and out['depth'].shape == (ro.shape[0],)
 
 

@@ -132,7 +132,8 @@ def test_edge_cases(cuda_device):
     kw = rays_for(st, 4, 4)[1]
     # empty batch
     e = torch.zeros(0, 3, device=dev)
-    out = m(e, e, e, **kw)
+    with torch.no_grad():                      # inference: the fused kernel (autograd on -> train_forward)
+        out = m(e, e, e, **kw)
     assert out['rgb_marched'].shape == (0, 3) and out['rgb_feature'] is out['rgb_marched']
     # rays that miss the box, axis-parallel rays (zero components -> the 1e-6 substitution), ragged N
     ro = torch.tensor([[0, 0, 4.], [5, 5, 5.], [0.3, -0.2, 4.], [0, 0, 0.]])
@@ -154,16 +155,18 @@ def test_forward_contract_and_scene_refresh(cuda_device):
     st = make_state('cfgA', res=24, regime='fog')
     m = model_from_state(st, dev)
     (ro, rd, vd), kw = rays_for(st, 8, 8)
-    out = m(ro.to(dev), rd.to(dev), vd.to(dev), **kw)
-    assert set(out) >= {'rgb_marched', 'rgb_feature', 'alphainv_last', 'depth'}
+    with torch.no_grad():
+        out = m(ro.to(dev), rd.to(dev), vd.to(dev), **kw)
+    assert set(out) >= {'rgb_marched', 'rgb_feature', 'alphainv_last', 'depth'} and 'weights' not in out
     assert out['rgb_feature'].data_ptr() == out['rgb_marched'].data_ptr()     # the reference's alias
     kw2 = dict(kw); kw2['render_depth'] = False
-    assert 'depth' not in m(ro.to(dev), rd.to(dev), vd.to(dev), **kw2)
+    with torch.no_grad():
+        assert 'depth' not in m(ro.to(dev), rd.to(dev), vd.to(dev), **kw2)
     # in-place parameter edits must invalidate the cached device scene
     before = out['rgb_marched'].clone()
     with torch.no_grad():
         m.density.grid.add_(3.0)
-    after = m(ro.to(dev), rd.to(dev), vd.to(dev), **kw)['rgb_marched']
+        after = m(ro.to(dev), rd.to(dev), vd.to(dev), **kw)['rgb_marched']
     assert (after - before).abs().max().item() > 1e-3
 
 

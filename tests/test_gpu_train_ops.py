@@ -1,0 +1,192 @@
+"""GPU: grid-maintenance and optimiser kernels (csrc/k4_train.cu).
+
+total_variation_add_grad and the three Adam updates are compared BIT FOR BIT with the reference's own
+extensions (oracle/_ref/total_variation_cuda.so, adam_upd_cuda.so, built by oracle/build_ref.py);
+update_occupancy_cache / scale_volume_grid are compared with the reference's torch composition
+(F.grid_sample + Raw2Alpha formula + F.max_pool3d, F.interpolate) run on the same GPU."""
+import os
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+import k4nerf
+from k4nerf import adam_upd_cuda, total_variation_cuda
+from helpers import make_state, model_from_state
+from oracle import ops
+
+pytestmark = pytest.mark.gpu
+
+
+def _ref(name):
+    path = os.path.join(os.path.dirname(ops.ref_ext_path()), name + '.so')
+    if not os.path.exists(path):
+        pytest.skip(f'oracle/_ref/{name}.so not built (python oracle/build_ref.py where /root/reference exists)')
+    return ops.load_ref_ext(name)
+
+
+@pytest.mark.parametrize('shape', [(1, 1, 17, 9, 33), (1, 12, 20, 24, 16), (1, 3, 1, 5, 2)])
+@pytest.mark.parametrize('dense', [True, False])
+def test_total_variation_add_grad_bit_exact(cuda_device, shape, dense):
+    ref = _ref('total_variation_cuda')
+    g = torch.Generator().manual_seed(3)
+    param = (torch.randn(shape, generator=g) * 1.5).to(cuda_device)
+    grad = torch.randn(shape, generator=g)
+    grad[torch.rand(shape, generator=g) < 0.6] = 0            # sparse gradients: the non-dense mode skips zeros
+    grad = grad.to(cuda_device)
+    ga, gb = grad.clone(), grad.clone()
+    total_variation_cuda.total_variation_add_grad(param, ga, 0.37, 1.1, 2.3e-3, dense)
+    ref.total_variation_add_grad(param, gb, 0.37, 1.1, 2.3e-3, dense)
+    torch.cuda.synchronize()
+    assert torch.equal(ga, gb)
+    assert not torch.equal(ga, grad)
+    if not dense:
+        assert torch.equal(ga[grad == 0], grad[grad == 0])
+
+
+@pytest.mark.parametrize('n', [4096 * 3, 1001])               # float4 path and the scalar tail path
+@pytest.mark.parametrize('variant', ['plain', 'masked', 'perlr'])
+def test_adam_updates_bit_exact(cuda_device, n, variant):
+    ref = _ref('adam_upd_cuda')
+    g = torch.Generator().manual_seed(7)
+    mk = lambda s=1.0: (torch.randn(n, generator=g) * s).to(cuda_device)
+    p0, m0, v0 = mk(), mk(0.1), (mk(0.1) ** 2)
+    perlr = torch.rand(n, generator=g).to(cuda_device)
+    ours, theirs = [p0.clone(), m0.clone(), v0.clone()], [p0.clone(), m0.clone(), v0.clone()]
+    for step in (1, 2, 7, 1000):
+        grad = torch.randn(n, generator=g)
+        grad[torch.rand(n, generator=g) < 0.7] = 0
+        grad = grad.to(cuda_device)
+        for mod, (p, m, v) in ((adam_upd_cuda, ours), (ref, theirs)):
+            if variant == 'plain':
+                mod.adam_upd(p, grad, m, v, step, 0.9, 0.99, 0.1, 1e-8)
+            elif variant == 'masked':
+                mod.masked_adam_upd(p, grad, m, v, step, 0.9, 0.99, 0.1, 1e-8)
+            else:
+                mod.adam_upd_with_perlr(p, grad, m, v, perlr, step, 0.9, 0.99, 0.1, 1e-8)
+        torch.cuda.synchronize()
+        for a, b, name in zip(ours, theirs, ('param', 'exp_avg', 'exp_avg_sq')):
+            assert torch.equal(a, b), (variant, step, name, (a - b).abs().max().item())
+    assert not torch.equal(ours[0], p0)
+
+
+def test_masked_adam_optimizer_matches_manual_updates(cuda_device):
+    """MaskedAdam.step dispatch (lib/masked_adam.py:41-73): per-voxel lr wins for the matching shape,
+    skip_zero_grad selects the masked kernel, state keys as the reference."""
+    g = torch.Generator().manual_seed(1)
+    a = torch.nn.Parameter(torch.randn(1, 1, 6, 5, 4, generator=g).to(cuda_device))
+    b = torch.nn.Parameter(torch.randn(33, generator=g).to(cuda_device))
+    opt = k4nerf.MaskedAdam([{'params': [a], 'lr': 0.1, 'skip_zero_grad': True}, {'params': [b], 'lr': 0.01, 'skip_zero_grad': False}])
+    a.grad = torch.zeros_like(a)
+    a.grad[0, 0, 1, 2, 3] = 2.0
+    b.grad = torch.ones_like(b)
+    a0, b0 = a.detach().clone(), b.detach().clone()
+    opt.step()
+    assert set(opt.state[a].keys()) == {'step', 'exp_avg', 'exp_avg_sq'} and opt.state[a]['step'] == 1
+    changed = (a.detach() != a0)
+    assert int(changed.sum()) == 1 and bool(changed[0, 0, 1, 2, 3])
+    assert torch.allclose(b.detach(), b0 - 0.01, atol=1e-6)           # first Adam step moves by lr * sign(g)
+    count = torch.zeros_like(a)
+    count[0, 0, 1, 2, 3] = 4.0
+    count[0, 0, 0, 0, 0] = 2.0
+    opt.set_pervoxel_lr(count)
+    a.grad = torch.ones_like(a)
+    a1 = a.detach().clone()
+    opt.step()
+    moved = (a.detach() != a1)
+    assert int(moved.sum()) == 2                                          # per-voxel lr 0 elsewhere
+
+
+def _torch_alpha(density, shift, interval):
+    return 1 - torch.pow(1 + torch.exp(density + shift), -interval)
+
+
+@pytest.mark.parametrize('name', ['cfgA', 'cfgB', 'cfgC'])
+def test_update_occupancy_cache_vs_torch_composition(cuda_device, name):
+    dev = cuda_device
+    st = make_state(name, regime='fog') if name != 'cfgB' else make_state(name, xy=40, depth=24, regime='fog')
+    m = model_from_state(st, dev)
+    with torch.no_grad():
+        m.density.grid.mul_(4.0).sub_(2.0)             # a spread of alphas around the threshold
+    mask0 = m.mask_cache.mask.clone()
+    # reference composition (lib/dvgo.py:224-233) with ATen ops on the same device
+    shp = mask0.shape
+    xyz = torch.stack(torch.meshgrid(*[torch.linspace(float(m.xyz_min[a]), float(m.xyz_max[a]), shp[a], device=dev) for a in range(3)],
+                                     indexing='ij'), -1)
+    ind = ((xyz.reshape(1, 1, 1, -1, 3) - m.xyz_min) / (m.xyz_max - m.xyz_min)).flip((-1,)) * 2 - 1
+    den = F.grid_sample(m.density.grid, ind, mode='bilinear', align_corners=True).reshape(shp)
+    shift = 0.0 if name == 'cfgB' else float(m.act_shift)
+    alpha = _torch_alpha(den, shift, float(m.voxel_size_ratio))
+    # threshold at the 98.5th percentile of the voxel alphas: after the 3x3x3 max-pool about a third stays occupied
+    thres = float(torch.quantile(alpha.flatten()[:1 << 20], 0.985))
+    m.fast_color_thres = thres
+    want = mask0 & (F.max_pool3d(alpha[None, None], kernel_size=3, padding=1, stride=1)[0, 0] > thres)
+    m.update_occupancy_cache()
+    got = m.mask_cache.mask
+    flips = int((got != want).sum())
+    assert flips <= max(1, int(1e-4 * got.numel())), (flips, got.numel())
+    assert 0 < int(got.sum()) < got.numel()            # the update really decided something both ways
+    # the next render sees the new mask
+    from helpers import rays_for
+    (ro, rd, vd), kw = rays_for(st, 16, 16)
+    out = m.render_rays(ro.to(dev), rd.to(dev), vd.to(dev), kw, debug=True)
+    assert out['rgb_marched'].isfinite().all()
+
+
+def test_resample_trilinear_vs_aten(cuda_device):
+    g = torch.Generator().manual_seed(4)
+    src = torch.randn(1, 5, 13, 9, 21, generator=g).to(cuda_device)
+    for size in ((20, 17, 33), (13, 9, 21), (7, 4, 11), (1, 1, 1)):
+        grid_ = k4nerf.grid.DenseGrid(5, list(src.shape[2:]), [-1, -1, -1], [1, 1, 1]).to(cuda_device)
+        grid_.grid.data.copy_(src)
+        grid_.scale_volume_grid(torch.tensor(size))
+        want = F.interpolate(src, size=size, mode='trilinear', align_corners=True)
+        assert grid_.grid.shape == want.shape
+        assert torch.allclose(grid_.grid.data, want, atol=2e-6, rtol=1e-6), (size, (grid_.grid.data - want).abs().max().item())
+
+
+def test_scale_volume_grid_end_to_end(cuda_device):
+    """DirectVoxGO.scale_volume_grid (lib/dvgo.py:200-221): new world size, resampled grids, rebuilt mask."""
+    dev = cuda_device
+    st = make_state('cfgA', res=24, regime='fog')
+    m = model_from_state(st, dev)
+    with torch.no_grad():
+        m.density.grid.mul_(4.0).sub_(2.0)
+    den0, k00, mask0 = m.density.grid.data.clone(), m.k0.grid.data.clone(), m.mask_cache.mask.clone()
+    m.scale_volume_grid(32 ** 3)
+    ws = m.world_size.tolist()
+    assert ws == [32, 32, 32] and list(m.density.grid.shape[2:]) == ws and list(m.k0.grid.shape[1:]) == [12] + ws
+    want_den = F.interpolate(den0, size=tuple(ws), mode='trilinear', align_corners=True)
+    assert torch.allclose(m.density.grid.data, want_den, atol=2e-6, rtol=1e-6)
+    assert torch.allclose(m.k0.grid.data, F.interpolate(k00, size=tuple(ws), mode='trilinear', align_corners=True), atol=2e-6, rtol=1e-6)
+    alpha = _torch_alpha(want_den, float(m.act_shift), float(m.voxel_size_ratio))
+    want_mask = F.max_pool3d(alpha, kernel_size=3, padding=1, stride=1)[0, 0] > float(m.fast_color_thres)   # old mask was all true
+    assert bool(mask0.all())
+    flips = int((m.mask_cache.mask != want_mask).sum())
+    assert flips <= max(1, int(1e-4 * want_mask.numel())), flips
+    assert list(m.mask_cache.mask.shape) == ws
+    from helpers import rays_for
+    (ro, rd, vd), kw = rays_for(st, 16, 16)
+    out = m.render_rays(ro.to(dev), rd.to(dev), vd.to(dev), kw)
+    assert out['rgb_marched'].isfinite().all()
+
+
+def test_total_variation_hooks(cuda_device):
+    dev = cuda_device
+    st = make_state('cfgA', res=16, regime='fog')
+    m = model_from_state(st, dev)
+    m.density.grid.grad = torch.zeros_like(m.density.grid)
+    m.k0.grid.grad = torch.zeros_like(m.k0.grid)
+    m.density_total_variation_add_grad(1e-3, True)
+    m.k0_total_variation_add_grad(1e-3, False)             # sparse mode with an all-zero grad: untouched
+    assert float(m.density.grid.grad.abs().sum()) > 0 and float(m.k0.grid.grad.abs().sum()) == 0
+    # dense TV gradient == autograd of the reference's loss definition: sum over neighbour pairs of
+    # huber(delta=1)(difference) * w/6 * 2 directions ... checked through the analytic form instead:
+    p = m.density.grid.data
+    w = float(1e-3 * m.world_size.max() / 128) / 6
+    want = torch.zeros_like(p)
+    for dim in (2, 3, 4):
+        d = (p.narrow(dim, 1, p.shape[dim] - 1) - p.narrow(dim, 0, p.shape[dim] - 1)).clamp(-1, 1) * w
+        want.narrow(dim, 1, p.shape[dim] - 1).add_(d)
+        want.narrow(dim, 0, p.shape[dim] - 1).sub_(d)
+    assert torch.allclose(m.density.grid.grad, want, atol=1e-7, rtol=1e-5)

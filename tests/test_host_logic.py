@@ -123,3 +123,23 @@ def test_dcvgo_constructor_contract():
     with pytest.raises(NotImplementedError):
         k4nerf.DirectContractedVoxGO(xyz_min=[-1] * 3, xyz_max=[1] * 3, num_voxels=8 ** 3, num_voxels_base=8 ** 3,
                                      alpha_init=1e-2, contracted_norm='l2')
+
+
+def test_masked_adam_argument_validation_and_training_modules_import():
+    """lib/masked_adam.py:19-30 argument checks; the drop-in module names of the reference's four CUDA
+    extensions all exist with the reference's function names."""
+    p = torch.nn.Parameter(torch.zeros(3))
+    for bad in (dict(lr=-1.0), dict(eps=-1e-8), dict(betas=(1.0, 0.99)), dict(betas=(0.9, -0.1))):
+        with pytest.raises(ValueError):
+            k4nerf.MaskedAdam([p], **bad)
+    opt = k4nerf.MaskedAdam([{'params': [p], 'skip_zero_grad': True}], lr=0.5)
+    assert opt.per_lr is None and opt.param_groups[0]['lr'] == 0.5 and opt.param_groups[0]['betas'] == (0.9, 0.99)
+    opt.step()                                                    # no grads: nothing to do, no GPU needed
+    from k4nerf import render_utils_cuda, total_variation_cuda, adam_upd_cuda, ub360_utils_cuda, autograd_ops
+    assert callable(total_variation_cuda.total_variation_add_grad) and callable(ub360_utils_cuda.cumdist_thres)
+    assert {'adam_upd', 'masked_adam_upd', 'adam_upd_with_perlr'} <= set(dir(adam_upd_cuda))
+    assert {'Raw2Alpha', 'Raw2Alpha_nonuni', 'Alphas2Weights'} <= set(dir(autograd_ops))
+    assert issubclass(autograd_ops.Raw2Alpha, torch.autograd.Function)
+    with pytest.raises(RuntimeError, match='CUDA'):
+        adam_upd_cuda.adam_upd(torch.zeros(4), torch.zeros(4), torch.zeros(4), torch.zeros(4), 1, 0.9, 0.99, 0.1, 1e-8)
+    assert len(render_utils_cuda.__doc__) > 0
