@@ -106,8 +106,11 @@ def test_update_occupancy_cache_vs_torch_composition(cuda_device, name):
     dev = cuda_device
     st = make_state(name, regime='fog') if name != 'cfgB' else make_state(name, xy=40, depth=24, regime='fog')
     m = model_from_state(st, dev)
-    with torch.no_grad():
-        m.density.grid.mul_(4.0).sub_(2.0)             # a spread of alphas around the threshold
+    with torch.no_grad():                              # a spread of alphas, none saturated at 1
+        if name == 'cfgB':
+            m.density.grid.sub_(8.0)                   # interval = 256/24: keep exp(d) small
+        else:
+            m.density.grid.mul_(4.0).sub_(2.0)
     mask0 = m.mask_cache.mask.clone()
     # reference composition (lib/dvgo.py:224-233) with ATen ops on the same device
     shp = mask0.shape
@@ -119,6 +122,7 @@ def test_update_occupancy_cache_vs_torch_composition(cuda_device, name):
     alpha = _torch_alpha(den, shift, float(m.voxel_size_ratio))
     # threshold at the 98.5th percentile of the voxel alphas: after the 3x3x3 max-pool about a third stays occupied
     thres = float(torch.quantile(alpha.flatten()[:1 << 20], 0.985))
+    assert 0 < thres < 0.5
     m.fast_color_thres = thres
     want = mask0 & (F.max_pool3d(alpha[None, None], kernel_size=3, padding=1, stride=1)[0, 0] > thres)
     m.update_occupancy_cache()
