@@ -65,6 +65,13 @@ __device__ __forceinline__ constexpr uint32_t umma_idesc(int m, int n) {
     // InstrDescriptor: c_format=F32 [4,6), a/b_format=F16 (0), K-major A/B, n>>3 [17,23), m>>4 [24,29)
     return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
+// One lane of a converged warp; see sr_elect_one (k4_sr.cu): MMAs issued under `if (elect)` compile to
+// back-to-back UTCHMMA, under `if (wt == 0)` each one is wrapped in a uniformisation loop.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t p;
+    asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xffffffff;\nselp.u32 %0, 1, 0, P;\n}\n" : "=r"(p));
+    return p != 0;
+}
 __device__ __forceinline__ void mma_ss(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
     asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
                  "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n}\n"
@@ -242,7 +249,8 @@ k4_march_ws_kernel(const __grid_constant__ K4Dev s, const __grid_constant__ K4Re
             tc_mbar_wait(&c->full_bar, full_ph); full_ph ^= 1;
             if (*reinterpret_cast<volatile unsigned int*>(&c->exit_flag)) break;
             const unsigned tile = nb % TC_TILES;
-            if (wt == 0) {
+            if (wt == 0) ++n_batches;
+            if (warp_in_wg == 0 && elect_one()) {
                 TC_FENCE_AFTER();
                 const uint32_t a_tile = ring_s + tile * Cfg::TILE_BYTES;
                 constexpr uint32_t idW = umma_idesc(128, W);
@@ -251,14 +259,13 @@ k4_march_ws_kernel(const __grid_constant__ K4Dev s, const __grid_constant__ K4Re
                     mma_ss(tbase + D1, umma_desc(a_tile + k * 256, KCH), umma_desc(w1_s + k * 256, KCH), idW, k > 0);
                 mma_ss(tbase + D1, umma_desc(ones_s, 2), umma_desc(b1_s, 2), idW, 1);
                 umma_commit(&c->mma_bar);
-                ++n_batches;
             }
             tc_mbar_wait(&c->mma_bar, mma_ph); mma_ph ^= 1;
             TC_FENCE_AFTER();
             epilogue_repack<W>(tlane + D1);
             TC_FENCE_BEFORE();
             named_bar(bar_id);
-            if (wt == 0) {
+            if (warp_in_wg == 0 && elect_one()) {
                 TC_FENCE_AFTER();
                 constexpr uint32_t idW = umma_idesc(128, W);
 #pragma unroll
@@ -272,7 +279,7 @@ k4_march_ws_kernel(const __grid_constant__ K4Dev s, const __grid_constant__ K4Re
             epilogue_repack<W>(tlane + D2);
             TC_FENCE_BEFORE();
             named_bar(bar_id);
-            if (wt == 0) {
+            if (warp_in_wg == 0 && elect_one()) {
                 TC_FENCE_AFTER();
                 constexpr uint32_t id16 = umma_idesc(128, 16);
 #pragma unroll

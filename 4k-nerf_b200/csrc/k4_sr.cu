@@ -23,6 +23,7 @@
 // Numerics: conv operands are fp16 (weights and activations), accumulation fp32 in TMEM, the
 // residual trunk and all SFT / CondNet math stay fp32.  (The reference itself runs these convs with
 // TF32 operands: torch.backends.cudnn.allow_tf32 defaults to True.)
+#include <cuda.h>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -44,6 +45,26 @@ __device__ __forceinline__ void sr_mma_ss(uint32_t d, uint64_t a, uint64_t b, ui
     asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
                  "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n}\n"
                  :: "r"(d), "l"(a), "l"(b), "r"(idesc), "r"(acc), "r"(0u) : "memory");
+}
+// Same MMA, executed by a converged warp: every lane runs the instruction stream (so the descriptors stay in
+// the uniform datapath and ptxas needs no per-lane uniformisation loop), lane `leader` alone issues.
+__device__ __forceinline__ void sr_mma_ss_warp(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc, uint32_t leader) {
+    asm volatile("{\n.reg .pred p, q;\nsetp.ne.b32 p, %4, 0;\nsetp.ne.b32 q, %6, 0;\n"
+                 "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n}\n"
+                 :: "r"(d), "l"(a), "l"(b), "r"(idesc), "r"(acc), "r"(0u), "r"(leader) : "memory");
+}
+__device__ __forceinline__ void sr_commit_warp(uint64_t* bar, uint32_t leader) {
+    asm volatile("{\n.reg .pred q;\nsetp.ne.b32 q, %1, 0;\n"
+                 "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n}\n" :: "r"(sr_s32(bar)), "r"(leader) : "memory");
+}
+// One lane of a CONVERGED warp.  Issuing tcgen05.mma under `if (elect)` instead of `if (tid == 0)` matters:
+// ptxas knows an elected region is single-threaded, keeps the descriptors in uniform registers and emits
+// back-to-back UTCHMMA; under a plain divergent branch it wraps every MMA in an ELECT / R2UR / BRA.U.ANY
+// uniformisation loop (~12 extra instructions per MMA on the one thread that paces the tensor pipe).
+__device__ __forceinline__ bool sr_elect_one() {
+    uint32_t p;
+    asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xffffffff;\nselp.u32 %0, 1, 0, P;\n}\n" : "=r"(p));
+    return p != 0;
 }
 __device__ __forceinline__ void sr_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" :: "r"(sr_s32(bar)) : "memory");
@@ -94,6 +115,7 @@ struct ConvParams {
     float* dst_f; const float* add_f;                              // fp32 [P,64]
     float* out_nchw; int n_valid;
     int tiles_x;
+    int use_tma;                                                   // conv3x3_ws_kernel: halo by TMA tensor copies (not with upsample)
 };
 
 template <int N>
@@ -247,6 +269,258 @@ __global__ void __launch_bounds__(128) conv3x3_tc_kernel(const __grid_constant__
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
     __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" :: "r"(tbase), "r"((uint32_t)TCOLS) : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------
+// conv3x3_ws_kernel<N>: the same implicit GEMM as conv3x3_tc_kernel, restructured the Blackwell way --
+// ONE persistent CTA per SM, warp specialised, fed through a deep shared-memory ring:
+//   warps 4-7  producers: cp.async the (16+2)x(32+2) halo of a 16-channel slice (two 8-channel planes,
+//              zero fill = the conv's padding, nearest-x2 folded into the addressing) plus that slice's
+//              nine [N][16] weight tiles into ring stage g % NST; a stage is published (mbarrier FULL)
+//              two stages behind the issue point, so every producer thread keeps three stages of
+//              copies in flight;
+//   warp 8     one elected thread issues 36 tcgen05.mma per stage (4 M tiles of 16x8 pixels x 9 taps,
+//              K = 16) -- four M tiles share every weight tile, which cuts the L2->SM weight traffic
+//              of the one-tile-per-CTA kernel by 4x -- and commits the stage back to the producers
+//              (mbarrier EMPTY) and, after the last slice, the accumulator set to the epilogue;
+//   warps 0-3  epilogue: thread = pixel, tcgen05.ld 16 columns at a time, bias / LeakyReLU / residual /
+//              stores exactly as conv3x3_tc_kernel; TMEM holds TWO accumulator sets (2 x 4 x N
+//              columns), so the epilogue of tile i overlaps the main loop of tile i+1.
+// Tiles (16 rows x 32 columns of output pixels) are dealt round-robin to the CTAs.
+// ---------------------------------------------------------------------------------------------
+constexpr int WS_TM = 4;
+constexpr int WS_TX = 8 * WS_TM, WS_HX = WS_TX + 2;            // 32 / 34
+constexpr int WS_ROW = WS_HX * 16;                             // 544 B
+constexpr int WS_PLANE = (SR_HY * WS_ROW + 127) / 128 * 128;   // 9856 B: 9792 B of pixels, padded so every plane is a 128-B aligned TMA destination
+constexpr int WS_A_STAGE = (SR_CK / 8) * WS_PLANE;             // 19712 B
+constexpr int WS_HALO = SR_HY * WS_HX * (SR_CK / 8);           // 1224 16-byte copies per stage
+constexpr int WS_HALO_PER_THREAD = (WS_HALO + 127) / 128;      // 10
+constexpr int WS_LAG = 2;
+constexpr int WS_THREADS = 288;
+
+template <int N> struct WsCfg {
+    static constexpr int B_TAP = N * SR_CK * 2;
+    static constexpr int B_STAGE = 9 * B_TAP;
+    static constexpr int STAGE = WS_A_STAGE + B_STAGE;
+    static constexpr int NST = (N >= 64) ? 5 : 6;
+    static constexpr int NACC = (N < 16) ? 16 : N;
+    static constexpr int TCOLS = 2 * WS_TM * NACC;              // 512 / 256 / 128
+    static constexpr int SMEM = NST * STAGE + 256;
+};
+
+__device__ __forceinline__ void ws_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" :: "r"(sr_s32(bar)) : "memory");
+}
+
+template <int N>
+__global__ void __launch_bounds__(WS_THREADS, 1) conv3x3_ws_kernel(const __grid_constant__ ConvParams p, const __grid_constant__ CUtensorMap tmap) {
+    using C = WsCfg<N>;
+    extern __shared__ __align__(1024) unsigned char smem[];
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + C::NST * C::STAGE);     // [NST] count 128 (producers)
+    uint64_t* empty = full + C::NST;                                             // [NST] count 1 (tcgen05.commit)
+    uint64_t* acc_full = empty + C::NST;                                         // [2]   count 1 (tcgen05.commit)
+    uint64_t* acc_empty = acc_full + 2;                                          // [2]   count 128 (epilogue)
+    uint32_t* tslot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int tiles_x = (p.W + WS_TX - 1) / WS_TX, tiles_y = (p.H + SR_TY - 1) / SR_TY;
+    const int n_tiles = tiles_x * tiles_y;
+    const int nchunks = p.cin / SR_CK;
+
+    if (tid == 0) {
+        for (int i = 0; i < C::NST; ++i) { sr_mbar_init(full + i, p.use_tma ? 1 : 128); sr_mbar_init(empty + i, 1); }
+        sr_mbar_init(acc_full + 0, 1); sr_mbar_init(acc_full + 1, 1);
+        sr_mbar_init(acc_empty + 0, 128); sr_mbar_init(acc_empty + 1, 128);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" :: "r"(sr_s32(tslot)), "r"((uint32_t)C::TCOLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    const uint32_t tbase = *tslot;
+
+    if (warp >= 4 && warp < 8 && p.use_tma) {
+        // ------------------------------ producer (TMA): one thread, three bulk copies per stage ------------------------------
+        // The activation buffer is a 3-D tensor (channel, x, y); a box of (8 channels, 34, 18) lands in shared
+        // memory as [hy][hx] x 16 B = one plane of the UMMA layout; out-of-range coordinates (the -1 halo ring,
+        // the tile overhang) are zero-filled by the copy engine = the convolution's zero padding.
+        if (tid == 128) {
+            unsigned g = 0;
+            const uint64_t tm = reinterpret_cast<uint64_t>(&tmap);
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
+                const int y0 = ty * SR_TY - 1, x0 = tx * WS_TX - 1;
+                for (int c = 0; c < nchunks; ++c, ++g) {
+                    const unsigned slot = g % C::NST;
+                    if (g >= (unsigned)C::NST) sr_mbar_wait(empty + slot, ((g / C::NST) - 1) & 1);
+                    const uint32_t bar = sr_s32(full + slot);
+                    const uint32_t A = sr_s32(smem + slot * C::STAGE);
+                    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" :: "r"(bar), "r"((uint32_t)((SR_CK / 8) * SR_HY * WS_ROW + C::B_STAGE)) : "memory");
+#pragma unroll
+                    for (int pl = 0; pl < SR_CK / 8; ++pl)
+                        asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n"
+                                     :: "r"(A + pl * WS_PLANE), "l"(tm), "r"(bar), "r"(c * SR_CK + pl * 8), "r"(x0), "r"(y0) : "memory");
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                                 :: "r"(A + WS_A_STAGE), "l"(p.wpack + (size_t)c * C::B_STAGE), "r"((uint32_t)C::B_STAGE), "r"(bar) : "memory");
+                }
+            }
+        }
+    } else if (warp >= 4 && warp < 8) {
+        // ------------------------------ producers (cp.async; nearest-x2 source addressing) ------------------------------
+        const int pt = tid - 128;
+        const int sW = p.upsample ? (p.W >> 1) : p.W;
+        unsigned g = 0;
+        auto publish = [&](unsigned gi) {
+            asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+            ws_arrive(full + gi % C::NST);
+        };
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
+            const int y0 = ty * SR_TY, x0 = tx * WS_TX;
+            long long soff[WS_HALO_PER_THREAD];               // element offset of this thread's halo copies (-1: zero fill)
+#pragma unroll
+            for (int j = 0; j < WS_HALO_PER_THREAD; ++j) {
+                const int i = pt + j * 128;
+                const int plane = i & 1, pix = i >> 1;
+                const int hy = pix / WS_HX, hx = pix - hy * WS_HX;
+                const int gy = y0 - 1 + hy, gx = x0 - 1 + hx;
+                const bool in = (i < WS_HALO) & (gy >= 0) & (gy < p.H) & (gx >= 0) & (gx < p.W);
+                const int sy = p.upsample ? (gy >> 1) : gy, sx = p.upsample ? (gx >> 1) : gx;
+                soff[j] = in ? ((long long)sy * sW + sx) * p.src_cstride + p.src_c0 + plane * 8 : -1;
+            }
+            for (int c = 0; c < nchunks; ++c, ++g) {
+                const unsigned slot = g % C::NST;
+                if (g >= (unsigned)C::NST) sr_mbar_wait(empty + slot, ((g / C::NST) - 1) & 1);
+                unsigned char* A = smem + slot * C::STAGE;
+#pragma unroll
+                for (int j = 0; j < WS_HALO_PER_THREAD; ++j) {
+                    const int i = pt + j * 128;
+                    if (i < WS_HALO) {
+                        const int plane = i & 1, pix = i >> 1;
+                        const int hy = pix / WS_HX, hx = pix - hy * WS_HX;
+                        const bool in = soff[j] >= 0;
+                        cp_async16(A + plane * WS_PLANE + hy * WS_ROW + hx * 16, in ? p.src + soff[j] + c * SR_CK : p.src, in ? 16 : 0);
+                    }
+                }
+                const unsigned char* wsrc = p.wpack + (size_t)c * C::B_STAGE;
+                unsigned char* B = A + WS_A_STAGE;
+                for (int i = pt; i < C::B_STAGE / 16; i += 128) cp_async16(B + i * 16, wsrc + i * 16, 16);
+                asm volatile("cp.async.commit_group;\n" ::: "memory");
+                if (g >= (unsigned)WS_LAG) {
+                    asm volatile("cp.async.wait_group %0;\n" :: "n"(WS_LAG) : "memory");
+                    publish(g - WS_LAG);
+                }
+            }
+        }
+        // drain: the last WS_LAG stages
+        if (g >= 2) { asm volatile("cp.async.wait_group 1;\n" ::: "memory"); publish(g - 2); }
+        if (g >= 1) { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); publish(g - 1); }
+    } else if (warp == 8) {
+        // ------------------------------ MMA issuer (one elected lane) ------------------------------
+        if (sr_elect_one()) {
+            const uint32_t idesc = sr_idesc(128, C::NACC);
+            unsigned g = 0, it = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+                const unsigned a = it & 1;
+                if (it >= 2) sr_mbar_wait(acc_empty + a, ((it >> 1) - 1) & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+                const uint32_t dacc = tbase + a * WS_TM * C::NACC;
+                for (int c = 0; c < nchunks; ++c, ++g) {
+                    const unsigned slot = g % C::NST;
+                    sr_mbar_wait(full + slot, (g / C::NST) & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+                    const uint32_t a0 = sr_s32(smem) + slot * C::STAGE;
+                    // descriptors differ from tap to tap only in the 14-bit start-address field: add constants
+                    const uint64_t ad0 = sr_desc(a0, WS_PLANE, WS_ROW);
+                    const uint64_t bd0 = sr_desc(a0 + WS_A_STAGE, 128, (SR_CK / 8) * 128);
+#pragma unroll
+                    for (int t = 0; t < 9; ++t) {
+                        const int dy = t / 3, dx = t - dy * 3;
+#pragma unroll
+                        for (int m = 0; m < WS_TM; ++m)
+                            sr_mma_ss(dacc + m * C::NACC, ad0 + (uint64_t)((dy * WS_ROW + (m * 8 + dx) * 16) >> 4),
+                                      bd0 + (uint64_t)((t * C::B_TAP) >> 4), idesc, (c | t) != 0);
+                    }
+                    sr_commit(empty + slot);
+                }
+                sr_commit(acc_full + a);
+            }
+        }
+    } else if (warp < 4) {
+        // ------------------------------ epilogue ------------------------------
+        const uint32_t tl = tbase + ((uint32_t)(warp * 32) << 16);
+        unsigned it = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+            const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
+            const int y0 = ty * SR_TY, x0 = tx * WS_TX;
+            const unsigned a = it & 1;
+            sr_mbar_wait(acc_full + a, (it >> 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+#pragma unroll 1
+            for (int m = 0; m < WS_TM; ++m) {
+                const int py = y0 + (tid >> 3), px = x0 + m * 8 + (tid & 7);
+                const bool inside = (py < p.H) & (px < p.W);
+                const size_t pix = (size_t)py * p.W + px;
+#pragma unroll
+                for (int c16 = 0; c16 < C::NACC / 16; ++c16) {
+                    uint32_t v[16];
+                    sr_ld16(tl + (a * WS_TM + m) * C::NACC + c16 * 16, v);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+                    if (!inside) continue;
+                    float o[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) o[j] = __uint_as_float(v[j]) + __ldg(p.bias + c16 * 16 + j);
+                    if (p.mode == SRM_STORE_F16) {
+                        if (p.lrelu > 0.f) {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) o[j] = o[j] > 0.f ? o[j] : o[j] * p.lrelu;
+                        }
+                        __half2 h[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) h[j] = __floats2half2_rn(o[2 * j], o[2 * j + 1]);
+                        uint4* d = reinterpret_cast<uint4*>(p.dst_h + pix * p.dst_cstride + p.dst_c0 + c16 * 16);
+                        d[0] = *reinterpret_cast<uint4*>(&h[0]);
+                        d[1] = *reinterpret_cast<uint4*>(&h[4]);
+                    } else if (p.mode == SRM_TRUNK) {
+                        const float4* ad = reinterpret_cast<const float4*>(p.add_f + pix * 64 + c16 * 16);
+                        float4* d = reinterpret_cast<float4*>(p.dst_f + pix * 64 + c16 * 16);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const float4 r = ad[q];
+                            d[q] = make_float4(o[4 * q] * p.scale + r.x, o[4 * q + 1] * p.scale + r.y, o[4 * q + 2] * p.scale + r.z, o[4 * q + 3] * p.scale + r.w);
+                        }
+                    } else if (p.mode == SRM_ADD_STORE_F16) {
+                        const float4* ad = reinterpret_cast<const float4*>(p.add_f + pix * 64 + c16 * 16);
+                        __half2 h[8];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const float4 r = ad[q];
+                            h[2 * q] = __floats2half2_rn(o[4 * q] + r.x, o[4 * q + 1] + r.y);
+                            h[2 * q + 1] = __floats2half2_rn(o[4 * q + 2] + r.z, o[4 * q + 3] + r.w);
+                        }
+                        uint4* d = reinterpret_cast<uint4*>(p.dst_h + pix * p.dst_cstride + p.dst_c0 + c16 * 16);
+                        d[0] = *reinterpret_cast<uint4*>(&h[0]);
+                        d[1] = *reinterpret_cast<uint4*>(&h[4]);
+                    } else if (p.mode == SRM_STORE_F32F16) {
+                        float4* d = reinterpret_cast<float4*>(p.dst_f + pix * 64 + c16 * 16);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) d[q] = make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+                    } else {  // SRM_OUT_NCHW
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            if (c16 * 16 + j < p.n_valid) p.out_nchw[(size_t)(c16 * 16 + j) * p.H * p.W + pix] = o[j];
+                    }
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+            ws_arrive(acc_empty + a);
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" :: "r"(tbase), "r"((uint32_t)C::TCOLS) : "memory");
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -408,7 +682,7 @@ __global__ void __launch_bounds__(128) sft_tc_kernel(const __grid_constant__ Sft
         asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
         __syncthreads();
-        if (tid == 0) {
+        if (warp == 0 && sr_elect_one()) {
             asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
             const uint32_t id64 = sr_idesc(128, 64);
             sr_mma_ss(tbase + D0, sr_desc(a_s, 128, 512), sr_desc(blob_s + BL.off_b0, 128, 512), id64, 0);
@@ -434,7 +708,7 @@ __global__ void __launch_bounds__(128) sft_tc_kernel(const __grid_constant__ Sft
         asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
         __syncthreads();
-        if (tid == 0) {
+        if (warp == 0 && sr_elect_one()) {
             asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
             const uint32_t idc = sr_idesc(128, COUT);
             sr_mma_ts(tbase + D1S, tbase + D0 + 0, sr_desc(blob_s + BL.off_b1s, 128, 512), idc, 0);
@@ -680,12 +954,85 @@ int launch_conv(const ConvParams& p, cudaStream_t s) {
     return K4_OK;
 }
 
+typedef CUresult (*k4_encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                       const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                       CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
+static k4_encode_tiled_fn sr_encode_tiled() {
+    static k4_encode_tiled_fn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<k4_encode_tiled_fn>(ptr);
+        else
+            cudaGetLastError();
+    }
+    return fn;
+}
+
+// (channel, x, y) view of the NHWC fp16 source starting at channel src_c0; box = one 8-channel halo plane
+static bool sr_make_tmap(const ConvParams& p, CUtensorMap* tm) {
+    k4_encode_tiled_fn enc = sr_encode_tiled();
+    if (!enc) return false;
+    const cuuint64_t gdim[3] = {(cuuint64_t)p.cin, (cuuint64_t)p.W, (cuuint64_t)p.H};
+    const cuuint64_t gstride[2] = {(cuuint64_t)p.src_cstride * 2, (cuuint64_t)p.W * p.src_cstride * 2};
+    const cuuint32_t box[3] = {8, (cuuint32_t)WS_HX, (cuuint32_t)SR_HY};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    void* base = const_cast<__half*>(p.src + p.src_c0);
+    if (((uintptr_t)base & 15) || (gstride[0] & 15)) return false;
+    return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, base, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+static bool sr_no_tma() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("K4_CONV_NO_TMA"); v = (e && e[0] == '1') ? 1 : 0; }
+    return v == 1;
+}
+
+template <int N>
+int launch_conv_ws(ConvParams p, cudaStream_t s) {
+    using C = WsCfg<N>;
+    static bool attr_set = false;
+    static int sms = 0;
+    if (!attr_set) {
+        K4_CUDA_TRY(cudaFuncSetAttribute(conv3x3_ws_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+        int dev = 0;
+        K4_CUDA_TRY(cudaGetDevice(&dev));
+        K4_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        attr_set = true;
+    }
+    alignas(64) CUtensorMap tm;
+    memset(&tm, 0, sizeof(tm));
+    p.use_tma = (!p.upsample && !sr_no_tma() && sr_make_tmap(p, &tm)) ? 1 : 0;
+    const int tiles = ((p.W + WS_TX - 1) / WS_TX) * ((p.H + SR_TY - 1) / SR_TY);
+    conv3x3_ws_kernel<N><<<(unsigned)(tiles < sms ? tiles : sms), WS_THREADS, C::SMEM, s>>>(p, tm);
+    K4_CUDA_TRY(cudaGetLastError());
+    return K4_OK;
+}
+
+// K4_CONV_V1=1 selects the one-tile-per-CTA kernel (kept as the A/B reference of the persistent one)
+static bool sr_use_v1() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("K4_CONV_V1"); v = (e && e[0] == '1') ? 1 : 0; }
+    return v == 1;
+}
+
 int run_conv(const SrConv& c, ConvParams p, cudaStream_t s) {
     p.wpack = c.wpack; p.bias = c.bias; p.cin = c.cin_pad;
     p.tiles_x = (p.W + SR_TX - 1) / SR_TX;
-    if (c.npad == 64) return launch_conv<64>(p, s);
-    if (c.npad == 32) return launch_conv<32>(p, s);
-    return launch_conv<16>(p, s);
+    if (sr_use_v1()) {
+        if (c.npad == 64) return launch_conv<64>(p, s);
+        if (c.npad == 32) return launch_conv<32>(p, s);
+        return launch_conv<16>(p, s);
+    }
+    if (c.npad == 64) return launch_conv_ws<64>(p, s);
+    if (c.npad == 32) return launch_conv_ws<32>(p, s);
+    return launch_conv_ws<16>(p, s);
 }
 
 template <int COUT>
