@@ -72,8 +72,10 @@ class DirectVoxGO(FusedRenderMixin, GridMaintenanceMixin, nn.Module):
         if mask_cache_world_size is None:
             mask_cache_world_size = self.world_size
         if mask_cache_path:
-            raise NotImplementedError('mask_cache_path (coarse-geometry checkpoint) is a training-time feature')
-        mask = torch.ones([int(w) for w in mask_cache_world_size], dtype=torch.bool)
+            from .maintain import mask_from_coarse_checkpoint
+            mask = mask_from_coarse_checkpoint(mask_cache_path, mask_cache_thres, self.xyz_min, self.xyz_max, mask_cache_world_size)
+        else:
+            mask = torch.ones([int(w) for w in mask_cache_world_size], dtype=torch.bool)
         self.mask_cache = grid.MaskGrid(path=None, mask=mask, xyz_min=self.xyz_min, xyz_max=self.xyz_max)
 
     def _set_grid_resolution(self, num_voxels):

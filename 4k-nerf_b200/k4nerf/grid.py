@@ -73,7 +73,16 @@ class MaskGrid(nn.Module):
     def __init__(self, path=None, mask_cache_thres=None, mask=None, xyz_min=None, xyz_max=None):
         super().__init__()
         if path is not None:
-            raise NotImplementedError('mask_cache_path (coarse-stage checkpoint) is a training-time feature')
+            # occupancy of a coarse-stage checkpoint (lib/grid.py:277-285): dilate the density by one voxel,
+            # alpha with the softplus form of the activation, threshold
+            import torch.nn.functional as F
+            st = torch.load(path, map_location='cpu', weights_only=False)
+            sd, kw = st['model_state_dict'], st['model_kwargs']
+            self.mask_cache_thres = mask_cache_thres
+            dens = F.max_pool3d(sd['density.grid'].float(), kernel_size=3, padding=1, stride=1)
+            alpha = 1 - torch.exp(-F.softplus(dens + sd['act_shift'].float()) * kw['voxel_size_ratio'])
+            mask = (alpha >= mask_cache_thres)[0, 0]
+            xyz_min, xyz_max = kw['xyz_min'], kw['xyz_max']
         mask = mask.bool()
         xyz_min = torch.as_tensor(xyz_min, dtype=torch.float32).cpu()
         xyz_max = torch.as_tensor(xyz_max, dtype=torch.float32).cpu()

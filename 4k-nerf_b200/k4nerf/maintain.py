@@ -20,6 +20,18 @@ def _linspaces(xyz_min, xyz_max, shape, device):
     return [torch.linspace(float(xyz_min[a]), float(xyz_max[a]), int(shape[a]), device=device) for a in range(3)]
 
 
+def mask_from_coarse_checkpoint(path, thres, xyz_min, xyz_max, mask_world_size):
+    """Initial occupancy of a fine-stage model: the coarse checkpoint's occupancy (MaskGrid(path=...))
+    sampled at this model's mask-grid points (lib/dvgo.py:134-145, lib/dmpigo.py:140-151).  The lookup is
+    the CUDA op, as in the reference (which builds these on its default CUDA device)."""
+    if not torch.cuda.is_available():
+        raise RuntimeError('mask_cache_path needs a CUDA device (maskcache_lookup has no CPU path)')
+    dev = torch.device('cuda', torch.cuda.current_device())
+    coarse = grid.MaskGrid(path=path, mask_cache_thres=thres).to(dev)
+    lx, ly, lz = _linspaces(xyz_min, xyz_max, mask_world_size, dev)
+    return coarse(torch.stack(torch.meshgrid(lx, ly, lz, indexing='ij'), -1)).cpu()
+
+
 class GridMaintenanceMixin:
     _k4_shift_in_alpha = True        # DirectMPIGO: activate_density uses shift 0 (lib/dmpigo.py:258-261)
 

@@ -194,3 +194,26 @@ def test_total_variation_hooks(cuda_device):
         want.narrow(dim, 1, p.shape[dim] - 1).add_(d)
         want.narrow(dim, 0, p.shape[dim] - 1).sub_(d)
     assert torch.allclose(m.density.grid.grad, want, atol=1e-7, rtol=1e-5)
+
+
+def test_mask_cache_path_constructor_branch(cuda_device, tmp_path):
+    """Fine-stage constructor with a coarse checkpoint (lib/dvgo.py:134-145, lib/grid.py:277-285): the mask is
+    the coarse occupancy (max-pooled density, softplus alpha >= thres) looked up at the fine mask grid."""
+    g = torch.Generator().manual_seed(8)
+    dens = torch.randn(1, 1, 10, 12, 9, generator=g) * 4 - 2
+    coarse = {'model_state_dict': {'density.grid': dens, 'act_shift': torch.tensor([-4.5951])},
+              'model_kwargs': {'voxel_size_ratio': 1.0, 'xyz_min': [-1.0, -1.0, -1.0], 'xyz_max': [1.0, 1.0, 1.0]}}
+    path = str(tmp_path / 'coarse_last.tar')
+    torch.save(coarse, path)
+    mg = k4nerf.grid.MaskGrid(path=path, mask_cache_thres=1e-3)
+    d = F.max_pool3d(dens, kernel_size=3, padding=1, stride=1)
+    want = (1 - torch.exp(-F.softplus(d - 4.5951) * 1.0) >= 1e-3)[0, 0]
+    assert torch.equal(mg.mask, want) and 0 < int(want.sum()) < want.numel()
+    m = k4nerf.DirectVoxGO(xyz_min=[-0.8, -0.8, -0.8], xyz_max=[0.8, 0.8, 0.8], num_voxels=16 ** 3, num_voxels_base=16 ** 3,
+                           alpha_init=1e-2, mask_cache_path=path, mask_cache_thres=1e-3, fast_color_thres=1e-4, rgbnet_dim=0)
+    ws = m.world_size.tolist()
+    assert list(m.mask_cache.mask.shape) == ws and m.get_kwargs()['mask_cache_path'] == path
+    # nearest-voxel lookup of the coarse mask at the fine grid's points (lib/grid.py:295-304)
+    pts = torch.stack(torch.meshgrid(*[torch.linspace(-0.8, 0.8, w) for w in ws], indexing='ij'), -1)
+    ijk = torch.round(pts * mg.xyz2ijk_scale + mg.xyz2ijk_shift).long()
+    assert torch.equal(m.mask_cache.mask, want[ijk[..., 0], ijk[..., 1], ijk[..., 2]])
