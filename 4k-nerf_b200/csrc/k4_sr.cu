@@ -296,7 +296,7 @@ constexpr int WS_A_STAGE = (SR_CK / 8) * WS_PLANE;             // 19712 B
 constexpr int WS_HALO = SR_HY * WS_HX * (SR_CK / 8);           // 1224 16-byte copies per stage
 constexpr int WS_HALO_PER_THREAD = (WS_HALO + 127) / 128;      // 10
 constexpr int WS_LAG = 2;
-constexpr int WS_THREADS = 288;
+constexpr int WS_THREADS = 320;                               // warps 0-3 epilogue, 4-7 epilogue (TMA) / producers (cp.async), 8 MMA, 9 TMA producer
 
 template <int N> struct WsCfg {
     static constexpr int B_TAP = N * SR_CK * 2;
@@ -305,7 +305,7 @@ template <int N> struct WsCfg {
     static constexpr int NST = (N >= 64) ? 5 : 6;
     static constexpr int NACC = (N < 16) ? 16 : N;
     static constexpr int TCOLS = 2 * WS_TM * NACC;              // 512 / 256 / 128
-    static constexpr int SMEM = NST * STAGE + 256;
+    static constexpr int SMEM = NST * STAGE + 512;              // + barriers (256 B) + bias (256 B)
 };
 
 __device__ __forceinline__ void ws_arrive(uint64_t* bar) {
@@ -321,7 +321,10 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv3x3_ws_kernel(const __grid_
     uint64_t* acc_full = empty + C::NST;                                         // [2]   count 1 (tcgen05.commit)
     uint64_t* acc_empty = acc_full + 2;                                          // [2]   count 128 (epilogue)
     uint32_t* tslot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+    float* sbias = reinterpret_cast<float*>(smem + C::NST * C::STAGE + 256);    // [64]
     const int tid = threadIdx.x, warp = tid >> 5;
+    const int n_epi = p.use_tma ? 256 : 128;                                     // epilogue threads (8 or 4 warps)
+    if (tid < 64) sbias[tid] = p.bias[tid];
     const int tiles_x = (p.W + WS_TX - 1) / WS_TX, tiles_y = (p.H + SR_TY - 1) / SR_TY;
     const int n_tiles = tiles_x * tiles_y;
     const int nchunks = p.cin / SR_CK;
@@ -329,7 +332,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv3x3_ws_kernel(const __grid_
     if (tid == 0) {
         for (int i = 0; i < C::NST; ++i) { sr_mbar_init(full + i, p.use_tma ? 1 : 128); sr_mbar_init(empty + i, 1); }
         sr_mbar_init(acc_full + 0, 1); sr_mbar_init(acc_full + 1, 1);
-        sr_mbar_init(acc_empty + 0, 128); sr_mbar_init(acc_empty + 1, 128);
+        sr_mbar_init(acc_empty + 0, n_epi); sr_mbar_init(acc_empty + 1, n_epi);
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     if (warp == 0) {
@@ -341,12 +344,12 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv3x3_ws_kernel(const __grid_
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
     const uint32_t tbase = *tslot;
 
-    if (warp >= 4 && warp < 8 && p.use_tma) {
+    if (warp == 9) {
         // ------------------------------ producer (TMA): one thread, three bulk copies per stage ------------------------------
         // The activation buffer is a 3-D tensor (channel, x, y); a box of (8 channels, 34, 18) lands in shared
         // memory as [hy][hx] x 16 B = one plane of the UMMA layout; out-of-range coordinates (the -1 halo ring,
         // the tile overhang) are zero-filled by the copy engine = the convolution's zero padding.
-        if (tid == 128) {
+        if (p.use_tma && tid == 288) {
             unsigned g = 0;
             const uint64_t tm = reinterpret_cast<uint64_t>(&tmap);
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -367,7 +370,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv3x3_ws_kernel(const __grid_
                 }
             }
         }
-    } else if (warp >= 4 && warp < 8) {
+    } else if (warp >= 4 && warp < 8 && !p.use_tma) {
         // ------------------------------ producers (cp.async; nearest-x2 source addressing) ------------------------------
         const int pt = tid - 128;
         const int sW = p.upsample ? (p.W >> 1) : p.W;
@@ -448,9 +451,17 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv3x3_ws_kernel(const __grid_
                 sr_commit(acc_full + a);
             }
         }
-    } else if (warp < 4) {
+    } else if (warp < 8) {
         // ------------------------------ epilogue ------------------------------
-        const uint32_t tl = tbase + ((uint32_t)(warp * 32) << 16);
+        // thread = pixel of an M tile (TMEM lane = 32*(warp%4) + lane).  With the TMA producer warps 4-7 are a
+        // second epilogue warpgroup: group 0 takes M tiles 0,1 and group 1 tiles 2,3.  Per M tile all the
+        // independent work is issued first -- the residual row (global, fp32) and every 16-column TMEM load --
+        // and waited for once, so a tile's epilogue costs a few memory latencies, not one per 16 channels.
+        constexpr int NCH = C::NACC / 16;
+        const int et = tid & 127, egrp = tid >> 7;
+        const int m_lo = p.use_tma ? egrp * (WS_TM / 2) : 0, m_hi = p.use_tma ? m_lo + WS_TM / 2 : WS_TM;
+        const uint32_t tl = tbase + ((uint32_t)((warp & 3) * 32) << 16);
+        const bool has_res = (p.mode == SRM_TRUNK) | (p.mode == SRM_ADD_STORE_F16);
         unsigned it = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
             const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
@@ -459,19 +470,26 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv3x3_ws_kernel(const __grid_
             sr_mbar_wait(acc_full + a, (it >> 1) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
 #pragma unroll 1
-            for (int m = 0; m < WS_TM; ++m) {
-                const int py = y0 + (tid >> 3), px = x0 + m * 8 + (tid & 7);
+            for (int m = m_lo; m < m_hi; ++m) {
+                const int py = y0 + (et >> 3), px = x0 + m * 8 + (et & 7);
                 const bool inside = (py < p.H) & (px < p.W);
                 const size_t pix = (size_t)py * p.W + px;
+                float4 res[NCH * 4];
+                if (has_res && inside) {
+                    const float4* ad = reinterpret_cast<const float4*>(p.add_f + pix * 64);
 #pragma unroll
-                for (int c16 = 0; c16 < C::NACC / 16; ++c16) {
-                    uint32_t v[16];
-                    sr_ld16(tl + (a * WS_TM + m) * C::NACC + c16 * 16, v);
-                    asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
-                    if (!inside) continue;
+                    for (int q = 0; q < NCH * 4; ++q) res[q] = __ldg(ad + q);
+                }
+                uint32_t v[NCH][16];
+#pragma unroll
+                for (int c16 = 0; c16 < NCH; ++c16) sr_ld16(tl + (a * WS_TM + m) * C::NACC + c16 * 16, v[c16]);
+                asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+                if (!inside) continue;
+#pragma unroll
+                for (int c16 = 0; c16 < NCH; ++c16) {
                     float o[16];
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) o[j] = __uint_as_float(v[j]) + __ldg(p.bias + c16 * 16 + j);
+                    for (int j = 0; j < 16; ++j) o[j] = __uint_as_float(v[c16][j]) + sbias[c16 * 16 + j];
                     if (p.mode == SRM_STORE_F16) {
                         if (p.lrelu > 0.f) {
 #pragma unroll
@@ -484,19 +502,17 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv3x3_ws_kernel(const __grid_
                         d[0] = *reinterpret_cast<uint4*>(&h[0]);
                         d[1] = *reinterpret_cast<uint4*>(&h[4]);
                     } else if (p.mode == SRM_TRUNK) {
-                        const float4* ad = reinterpret_cast<const float4*>(p.add_f + pix * 64 + c16 * 16);
                         float4* d = reinterpret_cast<float4*>(p.dst_f + pix * 64 + c16 * 16);
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
-                            const float4 r = ad[q];
+                            const float4 r = res[c16 * 4 + q];
                             d[q] = make_float4(o[4 * q] * p.scale + r.x, o[4 * q + 1] * p.scale + r.y, o[4 * q + 2] * p.scale + r.z, o[4 * q + 3] * p.scale + r.w);
                         }
                     } else if (p.mode == SRM_ADD_STORE_F16) {
-                        const float4* ad = reinterpret_cast<const float4*>(p.add_f + pix * 64 + c16 * 16);
                         __half2 h[8];
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
-                            const float4 r = ad[q];
+                            const float4 r = res[c16 * 4 + q];
                             h[2 * q] = __floats2half2_rn(o[4 * q] + r.x, o[4 * q + 1] + r.y);
                             h[2 * q + 1] = __floats2half2_rn(o[4 * q + 2] + r.z, o[4 * q + 3] + r.w);
                         }

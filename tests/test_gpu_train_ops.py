@@ -205,12 +205,12 @@ def test_mask_cache_path_constructor_branch(cuda_device, tmp_path):
               'model_kwargs': {'voxel_size_ratio': 1.0, 'xyz_min': [-1.0, -1.0, -1.0], 'xyz_max': [1.0, 1.0, 1.0]}}
     path = str(tmp_path / 'coarse_last.tar')
     torch.save(coarse, path)
-    mg = k4nerf.grid.MaskGrid(path=path, mask_cache_thres=1e-3)
+    mg = k4nerf.grid.MaskGrid(path=path, mask_cache_thres=0.5)
     d = F.max_pool3d(dens, kernel_size=3, padding=1, stride=1)
-    want = (1 - torch.exp(-F.softplus(d - 4.5951) * 1.0) >= 1e-3)[0, 0]
+    want = (1 - torch.exp(-F.softplus(d - 4.5951) * 1.0) >= 0.5)[0, 0]
     assert torch.equal(mg.mask, want) and 0 < int(want.sum()) < want.numel()
     m = k4nerf.DirectVoxGO(xyz_min=[-0.8, -0.8, -0.8], xyz_max=[0.8, 0.8, 0.8], num_voxels=16 ** 3, num_voxels_base=16 ** 3,
-                           alpha_init=1e-2, mask_cache_path=path, mask_cache_thres=1e-3, fast_color_thres=1e-4, rgbnet_dim=0)
+                           alpha_init=1e-2, mask_cache_path=path, mask_cache_thres=0.5, fast_color_thres=1e-4, rgbnet_dim=0)
     ws = m.world_size.tolist()
     assert list(m.mask_cache.mask.shape) == ws and m.get_kwargs()['mask_cache_path'] == path
     # nearest-voxel lookup of the coarse mask at the fine grid's points (lib/grid.py:295-304)
