@@ -654,7 +654,7 @@ struct SftTcParams {
 };
 
 template <int COUT>
-__global__ void __launch_bounds__(128) sft_tc_kernel(const __grid_constant__ SftTcParams p) {
+__global__ void __launch_bounds__(128, (COUT == 64) ? 2 : 4) sft_tc_kernel(const __grid_constant__ SftTcParams p) {
     extern __shared__ __align__(1024) unsigned char smem[];
     const SftBlob BL = sft_blob_layout(COUT);
     unsigned char* blob = smem;
@@ -683,18 +683,41 @@ __global__ void __launch_bounds__(128) sft_tc_kernel(const __grid_constant__ Sft
     const uint32_t blob_s = sr_s32(blob), a_s = sr_s32(atile);
     uint32_t ph = 0;
 
+    // Register software pipeline: the kernel is a chain of dependent phases per 128-pixel tile (cond -> GEMM 1 ->
+    // repack -> GEMM 2 -> modulate) with only 8-16 warps per SM, so every global load that is issued where it is
+    // needed costs a full memory latency.  The condition row of tile i+1 is loaded while tile i is processed and
+    // the x row of tile i is requested before its GEMMs, so both land behind the tensor-core phases.
+    float4 cnd[8];
+    auto load_cond = [&](int t) {
+        const long long px_ = (long long)t * 128 + tid;
+        const float4* cp = reinterpret_cast<const float4*>(p.cond + (px_ < p.P ? px_ : 0) * 32);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) cnd[k] = __ldg(cp + k);
+    };
+    if ((int)blockIdx.x < p.n_tiles) load_cond(blockIdx.x);
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
         const long long pix = (long long)tile * 128 + tid;
         const bool valid = pix < p.P;
-        {   // cond row -> fp16, canonical layout (row = tid, 4 chunks of 8 channels)
-            const float4* cp = reinterpret_cast<const float4*>(p.cond + (valid ? pix : 0) * 32);
+        // cond row -> fp16, canonical layout (row = tid, 4 chunks of 8 channels)
 #pragma unroll
-            for (int kc = 0; kc < 4; ++kc) {
-                const float4 a = __ldg(cp + 2 * kc), b = __ldg(cp + 2 * kc + 1);
-                __half2 h[4] = {__floats2half2_rn(a.x, a.y), __floats2half2_rn(a.z, a.w), __floats2half2_rn(b.x, b.y), __floats2half2_rn(b.z, b.w)};
-                *reinterpret_cast<uint4*>(atile + tc_canon_off(tid, kc, 4)) = *reinterpret_cast<uint4*>(h);
+        for (int kc = 0; kc < 4; ++kc) {
+            const float4 a = cnd[2 * kc], b = cnd[2 * kc + 1];
+            __half2 h[4] = {__floats2half2_rn(a.x, a.y), __floats2half2_rn(a.z, a.w), __floats2half2_rn(b.x, b.y), __floats2half2_rn(b.z, b.w)};
+            *reinterpret_cast<uint4*>(atile + tc_canon_off(tid, kc, 4)) = *reinterpret_cast<uint4*>(h);
+        }
+        uint4 xraw[COUT / 4];                                   // the x row: COUT fp32 (all of it) or COUT fp16 (first half)
+        if (valid) {
+            if (p.x_f) {
+                const uint4* xp = reinterpret_cast<const uint4*>(p.x_f + pix * 64);
+#pragma unroll
+                for (int q = 0; q < COUT / 4; ++q) xraw[q] = __ldg(xp + q);
+            } else {
+                const uint4* xp = reinterpret_cast<const uint4*>(p.x_h + pix * p.xh_cstride + p.xh_c0);
+#pragma unroll
+                for (int q = 0; q < COUT / 8; ++q) xraw[q] = xp[q];
             }
         }
+        if (tile + (int)gridDim.x < p.n_tiles) load_cond(tile + gridDim.x);
         asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
         __syncthreads();
@@ -746,12 +769,13 @@ __global__ void __launch_bounds__(128) sft_tc_kernel(const __grid_constant__ Sft
             if (!valid) continue;
             float x[16];
             if (p.x_f) {
-                const float4* xp = reinterpret_cast<const float4*>(p.x_f + pix * 64 + c16 * 16);
 #pragma unroll
-                for (int q = 0; q < 4; ++q) { const float4 t = __ldg(xp + q); x[4 * q] = t.x; x[4 * q + 1] = t.y; x[4 * q + 2] = t.z; x[4 * q + 3] = t.w; }
+                for (int q = 0; q < 4; ++q) {
+                    const uint4 t = xraw[c16 * 4 + q];
+                    x[4 * q] = __uint_as_float(t.x); x[4 * q + 1] = __uint_as_float(t.y); x[4 * q + 2] = __uint_as_float(t.z); x[4 * q + 3] = __uint_as_float(t.w);
+                }
             } else {
-                const uint4* xp = reinterpret_cast<const uint4*>(p.x_h + pix * p.xh_cstride + p.xh_c0 + c16 * 16);
-                const uint4 u0 = xp[0], u1 = xp[1];
+                const uint4 u0 = xraw[c16 * 2], u1 = xraw[c16 * 2 + 1];
                 const __half2* hp0 = reinterpret_cast<const __half2*>(&u0);
                 const __half2* hp1 = reinterpret_cast<const __half2*>(&u1);
 #pragma unroll
