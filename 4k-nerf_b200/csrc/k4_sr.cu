@@ -46,17 +46,6 @@ __device__ __forceinline__ void sr_mma_ss(uint32_t d, uint64_t a, uint64_t b, ui
                  "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n}\n"
                  :: "r"(d), "l"(a), "l"(b), "r"(idesc), "r"(acc), "r"(0u) : "memory");
 }
-// Same MMA, executed by a converged warp: every lane runs the instruction stream (so the descriptors stay in
-// the uniform datapath and ptxas needs no per-lane uniformisation loop), lane `leader` alone issues.
-__device__ __forceinline__ void sr_mma_ss_warp(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc, uint32_t leader) {
-    asm volatile("{\n.reg .pred p, q;\nsetp.ne.b32 p, %4, 0;\nsetp.ne.b32 q, %6, 0;\n"
-                 "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n}\n"
-                 :: "r"(d), "l"(a), "l"(b), "r"(idesc), "r"(acc), "r"(0u), "r"(leader) : "memory");
-}
-__device__ __forceinline__ void sr_commit_warp(uint64_t* bar, uint32_t leader) {
-    asm volatile("{\n.reg .pred q;\nsetp.ne.b32 q, %1, 0;\n"
-                 "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n}\n" :: "r"(sr_s32(bar)), "r"(leader) : "memory");
-}
 // One lane of a CONVERGED warp.  Issuing tcgen05.mma under `if (elect)` instead of `if (tid == 0)` matters:
 // ptxas knows an elected region is single-threaded, keeps the descriptors in uniform registers and emits
 // back-to-back UTCHMMA; under a plain divergent branch it wraps every MMA in an ELECT / R2UR / BRA.U.ANY
@@ -116,6 +105,11 @@ struct ConvParams {
     float* out_nchw; int n_valid;
     int tiles_x;
     int use_tma;                                                   // conv3x3_ws_kernel: halo by TMA tensor copies (not with upsample)
+    // conv3x3_ws_kernel only -- sub-pixel form of "nearest x2 + 3x3 conv": the convolution iterates over the SOURCE
+    // grid with `ntaps` (4) of the nine halo offsets and phase-combined weights, and writes output pixel
+    // (y*out_s + out_oy, x*out_s + out_ox) of an (H*out_s) x (W*out_s) destination.  Defaults: 9 taps, out_s = 1.
+    int ntaps; unsigned char tap_dy[9], tap_dx[9];
+    int out_s, out_oy, out_ox;
 };
 
 template <int N>
@@ -360,13 +354,14 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv3x3_ws_kernel(const __grid_
                     if (g >= (unsigned)C::NST) sr_mbar_wait(empty + slot, ((g / C::NST) - 1) & 1);
                     const uint32_t bar = sr_s32(full + slot);
                     const uint32_t A = sr_s32(smem + slot * C::STAGE);
-                    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" :: "r"(bar), "r"((uint32_t)((SR_CK / 8) * SR_HY * WS_ROW + C::B_STAGE)) : "memory");
+                    const uint32_t bbytes = (uint32_t)p.ntaps * C::B_TAP;
+                    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" :: "r"(bar), "r"((uint32_t)((SR_CK / 8) * SR_HY * WS_ROW) + bbytes) : "memory");
 #pragma unroll
                     for (int pl = 0; pl < SR_CK / 8; ++pl)
                         asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n"
                                      :: "r"(A + pl * WS_PLANE), "l"(tm), "r"(bar), "r"(c * SR_CK + pl * 8), "r"(x0), "r"(y0) : "memory");
                     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
-                                 :: "r"(A + WS_A_STAGE), "l"(p.wpack + (size_t)c * C::B_STAGE), "r"((uint32_t)C::B_STAGE), "r"(bar) : "memory");
+                                 :: "r"(A + WS_A_STAGE), "l"(p.wpack + (size_t)c * bbytes), "r"(bbytes), "r"(bar) : "memory");
                 }
             }
         }
@@ -407,9 +402,10 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv3x3_ws_kernel(const __grid_
                         cp_async16(A + plane * WS_PLANE + hy * WS_ROW + hx * 16, in ? p.src + soff[j] + c * SR_CK : p.src, in ? 16 : 0);
                     }
                 }
-                const unsigned char* wsrc = p.wpack + (size_t)c * C::B_STAGE;
+                const int bbytes = p.ntaps * C::B_TAP;
+                const unsigned char* wsrc = p.wpack + (size_t)c * bbytes;
                 unsigned char* B = A + WS_A_STAGE;
-                for (int i = pt; i < C::B_STAGE / 16; i += 128) cp_async16(B + i * 16, wsrc + i * 16, 16);
+                for (int i = pt; i < bbytes / 16; i += 128) cp_async16(B + i * 16, wsrc + i * 16, 16);
                 asm volatile("cp.async.commit_group;\n" ::: "memory");
                 if (g >= (unsigned)WS_LAG) {
                     asm volatile("cp.async.wait_group %0;\n" :: "n"(WS_LAG) : "memory");
@@ -440,11 +436,13 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv3x3_ws_kernel(const __grid_
                     const uint64_t bd0 = sr_desc(a0 + WS_A_STAGE, 128, (SR_CK / 8) * 128);
 #pragma unroll
                     for (int t = 0; t < 9; ++t) {
-                        const int dy = t / 3, dx = t - dy * 3;
+                        if (t < p.ntaps) {
+                            const uint32_t aoff = (uint32_t)(p.tap_dy[t] * WS_ROW + p.tap_dx[t] * 16) >> 4;
 #pragma unroll
-                        for (int m = 0; m < WS_TM; ++m)
-                            sr_mma_ss(dacc + m * C::NACC, ad0 + (uint64_t)((dy * WS_ROW + (m * 8 + dx) * 16) >> 4),
-                                      bd0 + (uint64_t)((t * C::B_TAP) >> 4), idesc, (c | t) != 0);
+                            for (int m = 0; m < WS_TM; ++m)
+                                sr_mma_ss(dacc + m * C::NACC, ad0 + (uint64_t)(aoff + m * 8), bd0 + (uint64_t)((t * C::B_TAP) >> 4),
+                                          idesc, (c | t) != 0);
+                        }
                     }
                     sr_commit(empty + slot);
                 }
@@ -473,7 +471,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv3x3_ws_kernel(const __grid_
             for (int m = m_lo; m < m_hi; ++m) {
                 const int py = y0 + (et >> 3), px = x0 + m * 8 + (et & 7);
                 const bool inside = (py < p.H) & (px < p.W);
-                const size_t pix = (size_t)py * p.W + px;
+                const size_t pix = (size_t)(py * p.out_s + p.out_oy) * ((size_t)p.W * p.out_s) + (size_t)(px * p.out_s + p.out_ox);
                 float4 res[NCH * 4];
                 if (has_res && inside) {
                     const float4* ad = reinterpret_cast<const float4*>(p.add_f + pix * 64);
@@ -908,12 +906,39 @@ __global__ void pack_conv3x3_kernel(const float* __restrict__ W, unsigned char* 
     *reinterpret_cast<__half*>(dst + off) = __float2half_rn(w);
 }
 
+// Sub-pixel weights of "nearest x2 upsample, then 3x3 conv": output pixel (2Y+py, 2X+px) only sees the 2x2
+// source pixels (Y+py-1..Y+py, X+px-1..X+px); each of them collects the kernel rows / columns that land on it
+// after upsampling: phase 0: {-1: k0, 0: k1+k2}, phase 1: {0: k0+k1, +1: k2}.  Packed as [slice][4 taps][NPAD][SR_CK]
+// (tap = 2*iy + ix); the sums are formed in fp32 and rounded to fp16 once.  4/9 of the MACs of the direct form.
+__global__ void pack_conv_phase_kernel(const float* __restrict__ W, unsigned char* __restrict__ dst,
+                                       int cout, int cin, int npad, int nslices, int py, int px) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = (long long)nslices * 4 * npad * SR_CK;
+    if (i >= total) return;
+    const int k = (int)(i % SR_CK);
+    long long r = i / SR_CK;
+    const int n = (int)(r % npad); r /= npad;
+    const int t = (int)(r % 4);
+    const int sl = (int)(r / 4);
+    const int ci = sl * SR_CK + k;
+    const int iy = t >> 1, ix = t & 1;
+    // kernel index range collected by source offset (phase + i - 1)
+    const int ky0 = (py == 0) ? (iy == 0 ? 0 : 1) : (iy == 0 ? 0 : 2), ky1 = (py == 0) ? (iy == 0 ? 0 : 2) : (iy == 0 ? 1 : 2);
+    const int kx0 = (px == 0) ? (ix == 0 ? 0 : 1) : (ix == 0 ? 0 : 2), kx1 = (px == 0) ? (ix == 0 ? 0 : 2) : (ix == 0 ? 1 : 2);
+    float w = 0.f;
+    if (n < cout && ci < cin)
+        for (int ky = ky0; ky <= ky1; ++ky)
+            for (int kx = kx0; kx <= kx1; ++kx) w += W[((size_t)n * cin + ci) * 9 + ky * 3 + kx];
+    const size_t off = ((size_t)sl * 4 + t) * (npad * SR_CK * 2) + tc_canon_off(n, k >> 3, SR_CK / 8) + (k & 7) * 2;
+    *reinterpret_cast<__half*>(dst + off) = __float2half_rn(w);
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-struct SrConv { unsigned char* wpack; float* bias; int cin_pad, cout, npad; };
+struct SrConv { unsigned char* wpack; float* bias; int cin_pad, cout, npad; unsigned char* wphase[4]; };
 struct SrSft { float* w; unsigned char* blob; int cout; };
 
 struct k4_srnet {
@@ -954,6 +979,20 @@ int make_conv(k4_srnet* n, SrConv& c, const float* w, const float* b, int cout, 
     const long long total = (long long)nsl * 9 * c.npad * SR_CK;
     pack_conv3x3_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(w, c.wpack, cout, cin, c.npad, nsl);
     K4_CUDA_TRY(cudaGetLastError());
+    return K4_OK;
+}
+
+// the four sub-pixel weight packs of a conv that follows a nearest-x2 upsampling (conv_up1 / conv_up2)
+int make_conv_phases(k4_srnet* n, SrConv& c, const float* w, int cout, int cin, cudaStream_t s) {
+    const int nsl = c.cin_pad / SR_CK;
+    const size_t bytes = (size_t)nsl * 4 * c.npad * SR_CK * 2;
+    const long long total = (long long)nsl * 4 * c.npad * SR_CK;
+    for (int ph = 0; ph < 4; ++ph) {
+        int st = sr_alloc(n, (void**)&c.wphase[ph], bytes);
+        if (st) return st;
+        pack_conv_phase_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(w, c.wphase[ph], cout, cin, c.npad, nsl, ph >> 1, ph & 1);
+        K4_CUDA_TRY(cudaGetLastError());
+    }
     return K4_OK;
 }
 
@@ -1063,7 +1102,13 @@ static bool sr_use_v1() {
 }
 
 int run_conv(const SrConv& c, ConvParams p, cudaStream_t s) {
-    p.wpack = c.wpack; p.bias = c.bias; p.cin = c.cin_pad;
+    if (!p.wpack) p.wpack = c.wpack;
+    p.bias = c.bias; p.cin = c.cin_pad;
+    if (p.ntaps == 0) {
+        p.ntaps = 9;
+        for (int t = 0; t < 9; ++t) { p.tap_dy[t] = (unsigned char)(t / 3); p.tap_dx[t] = (unsigned char)(t % 3); }
+    }
+    if (p.out_s == 0) p.out_s = 1;
     p.tiles_x = (p.W + SR_TX - 1) / SR_TX;
     if (sr_use_v1()) {
         if (c.npad == 64) return launch_conv<64>(p, s);
@@ -1073,6 +1118,21 @@ int run_conv(const SrConv& c, ConvParams p, cudaStream_t s) {
     if (c.npad == 64) return launch_conv_ws<64>(p, s);
     if (c.npad == 32) return launch_conv_ws<32>(p, s);
     return launch_conv_ws<16>(p, s);
+}
+
+// nearest-x2 + conv as four sub-pixel convolutions over the source grid (p.H x p.W = SOURCE size, dst is 2H x 2W)
+int run_conv_up2x(const SrConv& c, ConvParams p, cudaStream_t s) {
+    for (int ph = 0; ph < 4; ++ph) {
+        const int py = ph >> 1, px = ph & 1;
+        ConvParams q = p;
+        q.upsample = 0; q.wpack = c.wphase[ph];
+        q.ntaps = 4;
+        for (int t = 0; t < 4; ++t) { q.tap_dy[t] = (unsigned char)(py + (t >> 1)); q.tap_dx[t] = (unsigned char)(px + (t & 1)); }
+        q.out_s = 2; q.out_oy = py; q.out_ox = px;
+        const int st = run_conv(c, q, s);
+        if (st != K4_OK) return st;
+    }
+    return K4_OK;
 }
 
 template <int COUT>
@@ -1168,8 +1228,8 @@ extern "C" int k4_srnet_create(const k4_srnet_desc* d, k4_stream_t stream, k4_sr
     }
     SR_TRY(make_sft(n, n->sftbody, P + k, 64, s)); k += 8;
     SR_TRY(make_conv(n, n->conv_body, P[k], P[k + 1], 64, 64, s)); k += 2;
-    SR_TRY(make_conv(n, n->conv_up1, P[k], P[k + 1], 64, 64, s)); k += 2;
-    SR_TRY(make_conv(n, n->conv_up2, P[k], P[k + 1], 64, 64, s)); k += 2;
+    SR_TRY(make_conv(n, n->conv_up1, P[k], P[k + 1], 64, 64, s)); SR_TRY(make_conv_phases(n, n->conv_up1, P[k], 64, 64, s)); k += 2;
+    SR_TRY(make_conv(n, n->conv_up2, P[k], P[k + 1], 64, 64, s)); SR_TRY(make_conv_phases(n, n->conv_up2, P[k], 64, 64, s)); k += 2;
     SR_TRY(make_conv(n, n->conv_hr, P[k], P[k + 1], 64, 64, s)); k += 2;
     SR_TRY(make_conv(n, n->conv_last, P[k], P[k + 1], 3, 64, s)); k += 2;
 #undef SR_TRY
@@ -1266,9 +1326,17 @@ extern "C" int k4_srnet_forward(const k4_srnet* n, const float* d_x, const float
     {   // upsample x2 (nearest) + conv + lrelu, twice; conv_hr + lrelu; conv_last
         ConvParams p = c0; p.H = 2 * h; p.W = 2 * w; p.upsample = 1; p.src = bf; p.src_cstride = 64; p.mode = SRM_STORE_F16; p.lrelu = 0.2f;
         p.dst_h = up1; p.dst_cstride = 64;
-        SR_DO(run_conv(n->conv_up1, p, s));
-        p.H = 4 * h; p.W = 4 * w; p.src = up1; p.dst_h = up2;
-        SR_DO(run_conv(n->conv_up2, p, s));
+        if (sr_use_v1()) {
+            SR_DO(run_conv(n->conv_up1, p, s));
+            p.H = 4 * h; p.W = 4 * w; p.src = up1; p.dst_h = up2;
+            SR_DO(run_conv(n->conv_up2, p, s));
+        } else {
+            p.H = h; p.W = w;                                   // iterate over the SOURCE grid, write the 2x grid
+            SR_DO(run_conv_up2x(n->conv_up1, p, s));
+            p.H = 2 * h; p.W = 2 * w; p.src = up1; p.dst_h = up2;
+            SR_DO(run_conv_up2x(n->conv_up2, p, s));
+            p.H = 4 * h; p.W = 4 * w;
+        }
         p.upsample = 0; p.src = up2; p.dst_h = hr;
         SR_DO(run_conv(n->conv_hr, p, s));
         ConvParams q = c0; q.H = 4 * h; q.W = 4 * w; q.src = hr; q.src_cstride = 64; q.mode = SRM_OUT_NCHW; q.out_nchw = d_out; q.n_valid = 3;
