@@ -3,25 +3,26 @@
 // Replaces the reference's 229 cuDNN convolutions + torch.cat copies + F.interpolate + leaky_relu
 // launches per tile with
 //
-//   conv3x3_tc_kernel<N>   every 3x3 convolution as an im2col-free implicit GEMM on tcgen05:
-//       a CTA owns SR_TM side-by-side 16x8 pixel tiles (M = 128 rows = y*8+x each) that share every
-//       weight stage; per 32-channel slice of the input the (16+2)x(8*SR_TM+2) halo is staged ONCE in
-//       shared memory as four 8-channel planes
-//       [plane][hy][hx] x 16 B -- which IS the canonical K-major UMMA layout (core matrix = 8
-//       horizontally adjacent pixels, SBO = halo row pitch, LBO = plane pitch) -- so the nine taps
-//       are nine shared-memory descriptors that differ only in their start address
-//       (+dy*ROW + dx*16 B); weights are pre-packed per (slice, tap) as [N][16] K-major tiles;
-//       fp32 accumulators live in TMEM for the whole K loop (9 taps x Cin/16 MMAs), loads of slice
-//       c+1 (cp.async, zero-fill = the conv's zero padding) overlap the MMAs of slice c;
-//       dense-block concatenation is free (a conv reads channels [0,Cin) of the block's NHWC buffer
-//       and writes its growth channels behind them), nearest-x2 upsampling is folded into the halo
-//       addressing, bias / LeakyReLU / residual scaling / trunk update are the epilogue;
-//   sft_kernel             SFTLayer (lib/sr_esrnet.py:112-123): both 1x1-conv branches + modulation,
-//       one thread per pixel, weights in shared memory, fp32;
+//   conv3x3_ws_kernel<N>   every 3x3 convolution as an im2col-free implicit GEMM on tcgen05, one persistent
+//       warp-specialised CTA per SM (TMA producer thread / elected MMA lane / two epilogue warpgroups, 5-6 stage
+//       shared-memory ring, two TMEM accumulator sets).  The (16+2)x(32+2) halo of a 16-channel slice is staged
+//       as two 8-channel planes [plane][hy][hx] x 16 B -- which IS the canonical K-major UMMA layout (core
+//       matrix = 8 horizontally adjacent pixels, SBO = halo row pitch, LBO = plane pitch) -- so the taps are
+//       shared-memory descriptors that differ only in their start address; weights are pre-packed per
+//       (slice, tap) as [N][16] K-major tiles; fp32 accumulators live in TMEM for the whole K loop.
+//       Dense-block concatenation is free (a conv reads channels [0,Cin) of the block's NHWC buffer and
+//       writes its growth channels behind them); "nearest x2 then conv" runs in its sub-pixel form (four
+//       phase convolutions over the source grid, 2x2 taps, phase-combined weights); bias / LeakyReLU /
+//       residual scaling / trunk update are the epilogue.  See the comment at the kernel.
+//   conv3x3_tc_kernel<N>   the first version (one 16x8 tile per CTA, 2-stage cp.async), kept as the A/B
+//       reference of the persistent kernel (K4_CONV_V1=1);
+//   sft_tc_kernel<COUT>    SFTLayer (lib/sr_esrnet.py:112-123): both 1x1-conv branches as two chained K=32
+//       tcgen05 GEMMs per 128-pixel tile (A of the second from TMEM) + modulation as the epilogue;
+//       sft_kernel is its fp32 one-thread-per-pixel predecessor (K4_SFT_FP32=1);
 //   condnet_kernel         CondNet (lib/sr_esrnet.py:440-444), one thread per pixel, fp32.
 //
 // Numerics: conv operands are fp16 (weights and activations), accumulation fp32 in TMEM, the
-// residual trunk and all SFT / CondNet math stay fp32.  (The reference itself runs these convs with
+// residual trunk and all CondNet math stay fp32.  (The reference itself runs these convs with
 // TF32 operands: torch.backends.cudnn.allow_tf32 defaults to True.)
 #include <cuda.h>
 #include <cstdio>
