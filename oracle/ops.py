@@ -168,6 +168,36 @@ class CpuOps:
         return mask
 
 
+    # ---- training-side element-wise ops (in place on CPU tensors), SURVEY.md section 8 f-4 ----
+    @staticmethod
+    def total_variation_add_grad(param, grad, wx, wy, wz, dense_mode):
+        """total_variation_cuda.total_variation_add_grad (lib/cuda/total_variation.cpp:16-20)."""
+        assert param.dtype == torch.float32 and grad.dtype == torch.float32 and param.is_contiguous() and grad.is_contiguous()
+        _lib().k4o_total_variation_add_grad(_p(param), _p(grad), ctypes.c_float(wx), ctypes.c_float(wy), ctypes.c_float(wz),
+                                            ctypes.c_int(int(bool(dense_mode))), ctypes.c_int64(param.numel()),
+                                            ctypes.c_int64(param.shape[2]), ctypes.c_int64(param.shape[3]), ctypes.c_int64(param.shape[4]))
+
+    @staticmethod
+    def _adam(param, grad, exp_avg, exp_avg_sq, perlr, step, beta1, beta2, lr, eps, skip):
+        for t in (param, grad, exp_avg, exp_avg_sq):
+            assert t.dtype == torch.float32 and t.is_contiguous()
+        _lib().k4o_adam_upd(_p(param), _p(grad), _p(exp_avg), _p(exp_avg_sq), _p(perlr) if perlr is not None else None,
+                            ctypes.c_int64(param.numel()), ctypes.c_int(int(step)), ctypes.c_float(beta1), ctypes.c_float(beta2),
+                            ctypes.c_float(lr), ctypes.c_float(eps), ctypes.c_int(int(skip)))
+
+    @staticmethod
+    def adam_upd(param, grad, exp_avg, exp_avg_sq, step, beta1, beta2, lr, eps):
+        CpuOps._adam(param, grad, exp_avg, exp_avg_sq, None, step, beta1, beta2, lr, eps, 0)
+
+    @staticmethod
+    def masked_adam_upd(param, grad, exp_avg, exp_avg_sq, step, beta1, beta2, lr, eps):
+        CpuOps._adam(param, grad, exp_avg, exp_avg_sq, None, step, beta1, beta2, lr, eps, 1)
+
+    @staticmethod
+    def adam_upd_with_perlr(param, grad, exp_avg, exp_avg_sq, perlr, step, beta1, beta2, lr, eps):
+        CpuOps._adam(param, grad, exp_avg, exp_avg_sq, perlr.contiguous(), step, beta1, beta2, lr, eps, 0)
+
+
 def ref_ext_path():
     return os.path.join(HERE, '_ref', 'render_utils_cuda.so')
 

@@ -252,6 +252,53 @@ K4O_API void k4o_cumdist_thres(const float* dist, float thres, int64_t n_rays, i
 }
 
 /* ------------------------------------------------------------------------------------------
+ * Training-side element-wise kernels
+ * ------------------------------------------------------------------------------------------ */
+static inline float k4o_clamp1(float v) { return fminf(fmaxf(v, -1.f), 1.f); }
+
+/* lib/cuda/total_variation_kernel.cu:13-66.  Reference build: every term is a separate product added to a
+ * running sum that starts at +0 (read from its SASS), then grad += sum. */
+K4O_API void k4o_total_variation_add_grad(const float* param, float* grad, float wx, float wy, float wz, int dense_mode,
+                                          int64_t n, int64_t szi, int64_t szj, int64_t szk) {
+    wx /= 6; wy /= 6; wz /= 6;
+#pragma omp parallel for schedule(static)
+    for (int64_t idx = 0; idx < n; ++idx) {
+        const float g0 = grad[idx];
+        if (!dense_mode && g0 == 0.f) continue;
+        const int64_t k = idx % szk, j = idx / szk % szj, i = idx / szk / szj % szi;
+        const float p = param[idx];
+        float acc = 0.f;
+        acc = acc + ((k == 0) ? 0.f : wx * k4o_clamp1(p - param[idx - 1]));
+        acc = acc + ((k == szk - 1) ? 0.f : wx * k4o_clamp1(p - param[idx + 1]));
+        acc = acc + ((j == 0) ? 0.f : wy * k4o_clamp1(p - param[idx - szk]));
+        acc = acc + ((j == szj - 1) ? 0.f : wy * k4o_clamp1(p - param[idx + szk]));
+        acc = acc + ((i == 0) ? 0.f : wz * k4o_clamp1(p - param[idx - szk * szj]));
+        acc = acc + ((i == szi - 1) ? 0.f : wz * k4o_clamp1(p - param[idx + szk * szj]));
+        grad[idx] = g0 + acc;
+    }
+}
+
+/* lib/cuda/adam_upd_kernel.cu:8-136 (adam_upd / masked_adam_upd / adam_upd_with_perlr).  Reference build:
+ * m = fma(m, b1, (1-b1)*g); v = fma(v, b2, ((1-b2)*g)*g); p -= (step_size [* perlr]) * m / (sqrt(v) + eps),
+ * IEEE sqrt and division; step_size in fp32 on the host (:76). */
+K4O_API void k4o_adam_upd(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, const float* perlr, int64_t n,
+                          int step, float beta1, float beta2, float lr, float eps, int skip_zero_grad) {
+    const float step_size = lr * sqrtf(1 - powf(beta2, (float)step)) / (1 - powf(beta1, (float)step));
+    const float omb1 = 1.f - beta1, omb2 = 1.f - beta2;
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n; ++i) {
+        const float g = grad[i];
+        if (!perlr && skip_zero_grad && g == 0.f) continue;
+        const float m = fmaf(beta1, exp_avg[i], omb1 * g);
+        const float v = fmaf(beta2, exp_avg_sq[i], (omb2 * g) * g);
+        const float num = perlr ? (step_size * perlr[i]) * m : step_size * m;
+        exp_avg[i] = m;
+        exp_avg_sq[i] = v;
+        param[i] = param[i] - num / (sqrtf(v) + eps);
+    }
+}
+
+/* ------------------------------------------------------------------------------------------
  * Counting helper used for the roofline figure: S_m, S_d, S_c are the
  * number of samples reaching the mask lookup / density fetch / feature fetch.  Pure bookkeeping
  * on masks produced by the pipeline; no reference counterpart.

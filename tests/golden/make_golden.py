@@ -62,14 +62,18 @@ MARCHER_CASES = {
     'cfgA_shell': ('cfgA', dict(res=24, regime='shell'), (16, 20)),
     'cfgB_fog': ('cfgB', dict(xy=24, depth=16, regime='fog'), (12, 16)),
     'cfg1_fog': ('cfg1', dict(res=16), (16, 16)),
+    # DirectContractedVoxGO (f-3): camera inside the inner cube, both regimes
+    'cfgC_fog': ('cfgC', dict(res=24, regime='fog'), (12, 16), dict(radius=0.6)),
+    'cfgC_shell': ('cfgC', dict(res=24, regime='shell'), (12, 16), dict(radius=0.6)),
 }
 
 
 def make_marcher_golden():
     from helpers import make_state, rays_for
-    for name, (kind, kw, hw) in MARCHER_CASES.items():
+    for name, case in MARCHER_CASES.items():
+        kind, kw, hw = case[:3]
         st = make_state(kind, **kw)
-        (ro, rd, vd), rkw = rays_for(st, *hw)
+        (ro, rd, vd), rkw = rays_for(st, *hw, **(case[3] if len(case) > 3 else {}))
         stats = {}
         r = pipeline.forward(st, ro, rd, vd, ops.CpuOps, stats=stats, **rkw)
         out = {'rgb_marched': r['rgb_marched'].clone(), 'depth': r['depth'].clone(),

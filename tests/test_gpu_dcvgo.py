@@ -84,3 +84,18 @@ def test_dcvgo_no_rgbnet_and_ragged(cuda_device):
     m = model_from_state(st, dev)
     ours = m.render_rays(ro.to(dev), rd.to(dev), vd.to(dev), kw, mlp_mode='fp32', debug=True)
     _check(ours, ref, stats, ro.shape[0], 'fp32', 80.0)
+
+
+@pytest.mark.parametrize('regime', ['fog', 'shell'])
+def test_dcvgo_fused_vs_committed_golden(cuda_device, regime):
+    """tests/golden/marcher_cfgC_*.pt (oracle outputs, tests/golden/make_golden.py) -- no oracle run needed."""
+    gold = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', f'marcher_cfgC_{regime}.pt'),
+                      map_location='cpu', weights_only=False)
+    st = make_state('cfgC', res=24, regime=regime)
+    (ro, rd, vd), kw = rays_for(st, 12, 16, radius=0.6)
+    m = model_from_state(st, cuda_device)
+    ours = m.render_rays(ro.to(cuda_device), rd.to(cuda_device), vd.to(cuda_device), kw, mlp_mode='fp32', debug=True)
+    c = ours['counters'].cpu().tolist()
+    assert abs(c[0] - gold['stats']['S_m']) <= 2 and abs(c[2] - gold['stats']['S_c']) <= 2, (c, gold['stats'])
+    cmp = compare(ours, gold, ro.shape[0])
+    assert cmp['rgb_marched_psnr'] >= 80.0 and cmp['depth_psnr'] >= 80.0 and cmp['alphainv_last_maxabs'] <= 1e-5, cmp

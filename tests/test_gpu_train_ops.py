@@ -217,3 +217,41 @@ def test_mask_cache_path_constructor_branch(cuda_device, tmp_path):
     pts = torch.stack(torch.meshgrid(*[torch.linspace(-0.8, 0.8, w) for w in ws], indexing='ij'), -1)
     ijk = torch.round(pts * mg.xyz2ijk_scale + mg.xyz2ijk_shift).long()
     assert torch.equal(m.mask_cache.mask, want[ijk[..., 0], ijk[..., 1], ijk[..., 2]])
+
+
+@pytest.mark.parametrize('dense', [True, False])
+def test_total_variation_matches_c_oracle(cuda_device, dense):
+    """The same kernel against the CPU restatement (oracle/render_utils_ref.c) -- parity without oracle/_ref."""
+    g = torch.Generator().manual_seed(13)
+    param = torch.randn(1, 3, 9, 11, 7, generator=g) * 1.5
+    grad = torch.randn(param.shape, generator=g)
+    grad[torch.rand(param.shape, generator=g) < 0.5] = 0
+    want = grad.clone()
+    ops.CpuOps.total_variation_add_grad(param, want, 0.37, 1.1, 2.3e-3, dense)
+    got = grad.clone().to(cuda_device)
+    total_variation_cuda.total_variation_add_grad(param.to(cuda_device), got, 0.37, 1.1, 2.3e-3, dense)
+    assert torch.equal(got.cpu(), want)
+
+
+@pytest.mark.parametrize('variant', ['plain', 'masked', 'perlr'])
+def test_adam_matches_c_oracle(cuda_device, variant):
+    g = torch.Generator().manual_seed(17)
+    n = 4096 + 3
+    p, m, v = torch.randn(n, generator=g), torch.randn(n, generator=g) * 0.1, (torch.randn(n, generator=g) * 0.1) ** 2
+    perlr = torch.rand(n, generator=g)
+    gp, gm, gv, gl = p.to(cuda_device), m.to(cuda_device), v.to(cuda_device), perlr.to(cuda_device)
+    for step in (1, 5, 200):
+        grad = torch.randn(n, generator=g)
+        grad[torch.rand(n, generator=g) < 0.7] = 0
+        gg = grad.to(cuda_device)
+        if variant == 'plain':
+            ops.CpuOps.adam_upd(p, grad, m, v, step, 0.9, 0.99, 0.1, 1e-8)
+            adam_upd_cuda.adam_upd(gp, gg, gm, gv, step, 0.9, 0.99, 0.1, 1e-8)
+        elif variant == 'masked':
+            ops.CpuOps.masked_adam_upd(p, grad, m, v, step, 0.9, 0.99, 0.1, 1e-8)
+            adam_upd_cuda.masked_adam_upd(gp, gg, gm, gv, step, 0.9, 0.99, 0.1, 1e-8)
+        else:
+            ops.CpuOps.adam_upd_with_perlr(p, grad, m, v, perlr, step, 0.9, 0.99, 0.1, 1e-8)
+            adam_upd_cuda.adam_upd_with_perlr(gp, gg, gm, gv, gl, step, 0.9, 0.99, 0.1, 1e-8)
+        for a, b, name in ((p, gp, 'param'), (m, gm, 'exp_avg'), (v, gv, 'exp_avg_sq')):
+            assert torch.equal(a, b.cpu()), (variant, step, name)

@@ -50,15 +50,18 @@ CASES = {
     'cfgA_shell': ('cfgA', dict(res=24, regime='shell'), (16, 20)),
     'cfgB_fog': ('cfgB', dict(xy=24, depth=16, regime='fog'), (12, 16)),
     'cfg1_fog': ('cfg1', dict(res=16), (16, 16)),
+    # DirectContractedVoxGO (f-3): camera inside the inner cube, both regimes
+    'cfgC_fog': ('cfgC', dict(res=24, regime='fog'), (12, 16), dict(radius=0.6)),
+    'cfgC_shell': ('cfgC', dict(res=24, regime='shell'), (12, 16), dict(radius=0.6)),
 }
 
 
 @pytest.mark.parametrize('name', sorted(CASES))
 def test_marcher_oracle_matches_golden(name):
-    kind, kw, hw = CASES[name]
+    kind, kw, hw = CASES[name][:3]
     gold = _load(f'marcher_{name}.pt')
     st = make_state(kind, **kw)
-    (ro, rd, vd), rkw = rays_for(st, *hw)
+    (ro, rd, vd), rkw = rays_for(st, *hw, **(CASES[name][3] if len(CASES[name]) > 3 else {}))
     stats = {}
     r = pipeline.forward(st, ro, rd, vd, ops.CpuOps, stats=stats, **rkw)
     assert stats == gold['stats']
@@ -134,3 +137,65 @@ def test_dcvgo_oracle_runs_and_is_deterministic():
     b = pipeline.forward(st, ro, rd, vd, ops.CpuOps, stats=s2, **kw)
     assert torch.equal(a['rgb_marched'], b['rgb_marched']) and s1 == s2
     assert 0 < s1['S_c'] <= s1['S_d'] <= s1['S_m'] and a['depth'].min() >= 0 and a['depth'].max() <= 1
+
+
+def test_total_variation_oracle_vs_numpy():
+    """k4o_total_variation_add_grad against an independent numpy statement of the clamped-difference TV
+    gradient (lib/cuda/total_variation_kernel.cu:13-38)."""
+    import numpy as np
+    g = torch.Generator().manual_seed(2)
+    p = (torch.randn(1, 2, 5, 4, 6, generator=g) * 1.5)
+    grad0 = torch.randn(p.shape, generator=g)
+    grad0[torch.rand(p.shape, generator=g) < 0.5] = 0
+    for dense in (True, False):
+        got = grad0.clone()
+        ops.CpuOps.total_variation_add_grad(p.contiguous(), got, 0.6, 1.2, 0.3, dense)
+        P = p.numpy().astype(np.float32)
+        want = grad0.numpy().copy()
+        w = [np.float32(0.3) / np.float32(6), np.float32(1.2) / np.float32(6), np.float32(0.6) / np.float32(6)]   # axis 2 (i): wz ... axis 4 (k): wx
+        w = {2: np.float32(0.3 / 1) / np.float32(6), 3: np.float32(1.2) / np.float32(6), 4: np.float32(0.6) / np.float32(6)}
+        add = np.zeros_like(P)
+        for ax in (4, 3, 2):                                   # the kernel adds k, then j, then i terms
+            for sgn in (-1, +1):                               # minus neighbour first, then plus neighbour
+                nb = np.roll(P, -sgn, axis=ax)
+                term = w[ax] * np.clip(P - nb, -1, 1)
+                idx = [slice(None)] * 5
+                idx[ax] = 0 if sgn == -1 else P.shape[ax] - 1
+                term[tuple(idx)] = 0
+                add = (add + term).astype(np.float32)
+        want2 = want + add
+        if not dense:
+            want2 = np.where(want == 0, want, want2)
+        assert np.array_equal(got.numpy(), want2.astype(np.float32)), dense
+
+
+def test_adam_oracle_vs_numpy():
+    """k4o_adam_upd (three variants) against numpy float32 arithmetic with the reference's expression shapes
+    (lib/cuda/adam_upd_kernel.cu:19-23,76)."""
+    import numpy as np
+    f = np.float32
+    g = torch.Generator().manual_seed(4)
+    n = 257
+    p0, m0, v0 = torch.randn(n, generator=g), torch.randn(n, generator=g) * 0.1, (torch.randn(n, generator=g) * 0.1) ** 2
+    grad = torch.randn(n, generator=g)
+    grad[torch.rand(n, generator=g) < 0.6] = 0
+    perlr = torch.rand(n, generator=g)
+    b1, b2, lr, eps, step = f(0.9), f(0.99), f(0.1), f(1e-8), 3
+    ss = f(lr * f(np.sqrt(f(1 - f(np.power(b2, f(step)))))) / f(1 - f(np.power(b1, f(step)))))
+    G = grad.numpy()
+    m = np.array([f(np.float64(b1) * np.float64(a) + np.float64(f(f(1) - b1) * gg)) for a, gg in zip(m0.numpy(), G)], dtype=np.float32)   # fma
+    v = np.array([f(np.float64(b2) * np.float64(a) + np.float64(f(f(f(1) - b2) * gg) * gg)) for a, gg in zip(v0.numpy(), G)], dtype=np.float32)
+    for variant in ('plain', 'masked', 'perlr'):
+        p, mm, vv = p0.clone(), m0.clone(), v0.clone()
+        if variant == 'plain':
+            ops.CpuOps.adam_upd(p, grad, mm, vv, step, float(b1), float(b2), float(lr), float(eps))
+        elif variant == 'masked':
+            ops.CpuOps.masked_adam_upd(p, grad, mm, vv, step, float(b1), float(b2), float(lr), float(eps))
+        else:
+            ops.CpuOps.adam_upd_with_perlr(p, grad, mm, vv, perlr, step, float(b1), float(b2), float(lr), float(eps))
+        num = (f(ss) * perlr.numpy()) * m if variant == 'perlr' else f(ss) * m
+        pw = (p0.numpy() - (num / (np.sqrt(v) + eps)).astype(np.float32)).astype(np.float32)
+        touched = (G != 0) if variant == 'masked' else np.ones(n, bool)
+        assert np.array_equal(mm.numpy(), np.where(touched, m, m0.numpy())), variant
+        assert np.array_equal(vv.numpy(), np.where(touched, v, v0.numpy())), variant
+        assert np.array_equal(p.numpy(), np.where(touched, pw, p0.numpy())), variant
