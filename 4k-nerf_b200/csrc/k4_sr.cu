@@ -539,6 +539,204 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv3x3_ws_kernel(const __grid_
 }
 
 // ---------------------------------------------------------------------------------------------
+// conv3x3_k64_kernel<N>: the 64-input-channel convolutions (conv_body, conv_up1/2 phases, conv_hr, conv_last --
+// every layer after the dense blocks, i.e. all the high-resolution work) with 128-BYTE shared-memory rows.
+// profiles/r1_conv_ws_ncu.md: those layers are bound by the copy engine's row rate -- conv3x3_ws_kernel moves a
+// 16-channel slice as 612 rows of 16 B per plane.  Here a pixel's 64 channels are ONE 128-byte row in the
+// SWIZZLE_128B K-major layout: the whole (16+2) x (24+2) halo of a tile is a single TMA tensor copy of 468 rows,
+// the nine taps are still nothing but descriptor start addresses (+ (dy*26 + dx) * 128 B; tools/micro/
+// conv_sw128_probe.cu shows that tap-shifted SW128 descriptors are exact with base_offset 0), a k16 step is
+// +32 B inside the row, and -- because Cin = 64 is a single K slice -- the layer's weights ([tap][n][64] fp16,
+// 74 KB for N = 64) are loaded ONCE per persistent CTA and stay resident.  Roles and barriers as in
+// conv3x3_ws_kernel (producer thread / elected MMA lane / two epilogue warpgroups, two TMEM accumulator sets).
+// ---------------------------------------------------------------------------------------------
+constexpr int K64_TM = 3;                                       // 16 x 24 output pixels per tile
+constexpr int K64_TX = 8 * K64_TM, K64_HX = K64_TX + 2;         // 24 / 26
+constexpr int K64_ROWB = 128;                                   // bytes per pixel row (64 fp16)
+constexpr int K64_A_BYTES = SR_HY * K64_HX * K64_ROWB;          // 59904: what one TMA copy delivers
+constexpr int K64_A_STAGE = (K64_A_BYTES + 1023) / 1024 * 1024; // 60416
+constexpr int K64_THREADS = 320;
+
+template <int N> struct K64Cfg {
+    static constexpr int NACC = N;                               // 64 or 16
+    static constexpr int B_TAP = N * K64_ROWB;                   // 8192 / 2048 (1024-aligned)
+    static constexpr int B_BYTES = 9 * B_TAP;
+    static constexpr int NST = (N >= 64) ? 2 : 3;
+    static constexpr int TCOLS = (2 * K64_TM * NACC <= 128) ? 128 : 512;   // 96 -> 128, 384 -> 512
+    static constexpr int SMEM = 1024 + B_BYTES + NST * K64_A_STAGE + 512;   // alignment slack + B + ring + barriers/bias
+};
+
+__device__ __forceinline__ uint64_t k64_desc(uint32_t saddr, uint32_t sbo_bytes) {      // SWIZZLE_128B, K-major, base_offset 0
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+
+template <int N>
+__global__ void __launch_bounds__(K64_THREADS, 1) conv3x3_k64_kernel(const __grid_constant__ ConvParams p, const __grid_constant__ CUtensorMap tmap_a,
+                                                                      const __grid_constant__ CUtensorMap tmap_b) {
+    using C = K64Cfg<N>;
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    unsigned char* Bw = smem;                                                    // [9][N][128 B] swizzled
+    unsigned char* Ar = smem + C::B_BYTES;                                       // ring of NST halo stages
+    uint64_t* full = reinterpret_cast<uint64_t*>(Ar + C::NST * K64_A_STAGE);    // [NST] count 1 + tx
+    uint64_t* empty = full + C::NST;                                             // [NST] count 1 (tcgen05.commit)
+    uint64_t* acc_full = empty + C::NST;                                         // [2]
+    uint64_t* acc_empty = acc_full + 2;                                          // [2] count 256
+    uint64_t* wbar = acc_empty + 2;                                              // weights landed
+    uint32_t* tslot = reinterpret_cast<uint32_t*>(wbar + 1);
+    float* sbias = reinterpret_cast<float*>(Ar + C::NST * K64_A_STAGE + 256);   // [64]
+    const int tid = threadIdx.x, warp = tid >> 5;
+    if (tid < 64) sbias[tid] = p.bias[tid];
+    const int tiles_x = (p.W + K64_TX - 1) / K64_TX, tiles_y = (p.H + SR_TY - 1) / SR_TY;
+    const int n_tiles = tiles_x * tiles_y;
+
+    if (tid == 0) {
+        for (int i = 0; i < C::NST; ++i) { sr_mbar_init(full + i, 1); sr_mbar_init(empty + i, 1); }
+        sr_mbar_init(acc_full + 0, 1); sr_mbar_init(acc_full + 1, 1);
+        sr_mbar_init(acc_empty + 0, 256); sr_mbar_init(acc_empty + 1, 256);
+        sr_mbar_init(wbar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" :: "r"(sr_s32(tslot)), "r"((uint32_t)C::TCOLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    const uint32_t tbase = *tslot;
+
+    if (warp == 9) {
+        // ------------------------------ producer: weights once, then one tensor copy per tile ------------------------------
+        if (tid == 288) {
+            const uint64_t ta = reinterpret_cast<uint64_t>(&tmap_a), tb = reinterpret_cast<uint64_t>(&tmap_b);
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" :: "r"(sr_s32(wbar)), "r"((uint32_t)p.ntaps * C::B_TAP) : "memory");
+            for (int t = 0; t < p.ntaps; ++t)
+                asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n"
+                             :: "r"(sr_s32(Bw + t * C::B_TAP)), "l"(tb), "r"(sr_s32(wbar)), "r"(0), "r"(t * N) : "memory");
+            unsigned g = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++g) {
+                const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
+                const unsigned slot = g % C::NST;
+                if (g >= (unsigned)C::NST) sr_mbar_wait(empty + slot, ((g / C::NST) - 1) & 1);
+                const uint32_t bar = sr_s32(full + slot);
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" :: "r"(bar), "r"((uint32_t)K64_A_BYTES) : "memory");
+                asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n"
+                             :: "r"(sr_s32(Ar + slot * K64_A_STAGE)), "l"(ta), "r"(bar), "r"(0), "r"(tx * K64_TX - 1), "r"(ty * SR_TY - 1) : "memory");
+            }
+        }
+    } else if (warp == 8) {
+        // ------------------------------ MMA issuer (one elected lane) ------------------------------
+        if (sr_elect_one()) {
+            const uint32_t idesc = sr_idesc(128, C::NACC);
+            sr_mbar_wait(wbar, 0);
+            unsigned g = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++g) {
+                const unsigned a = g & 1, slot = g % C::NST;
+                if (g >= 2) sr_mbar_wait(acc_empty + a, ((g >> 1) - 1) & 1);
+                sr_mbar_wait(full + slot, (g / C::NST) & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+                const uint64_t ad0 = k64_desc(sr_s32(Ar + slot * K64_A_STAGE), K64_HX * K64_ROWB);
+                const uint64_t bd0 = k64_desc(sr_s32(Bw), 1024);
+                const uint32_t dacc = tbase + a * K64_TM * C::NACC;
+#pragma unroll
+                for (int t = 0; t < 9; ++t) {
+                    if (t < p.ntaps) {
+                        const uint32_t aoff = (uint32_t)((p.tap_dy[t] * K64_HX + p.tap_dx[t]) * K64_ROWB) >> 4;
+#pragma unroll
+                        for (int m = 0; m < K64_TM; ++m)
+#pragma unroll
+                            for (int ks = 0; ks < 4; ++ks)
+                                sr_mma_ss(dacc + m * C::NACC, ad0 + (uint64_t)(aoff + m * 8 * (K64_ROWB >> 4) + ks * 2),
+                                          bd0 + (uint64_t)(((t * C::B_TAP) >> 4) + ks * 2), idesc, (t | ks) != 0);
+                    }
+                }
+                sr_commit(empty + slot);
+                sr_commit(acc_full + a);
+            }
+        }
+    } else {
+        // ------------------------------ epilogue: 8 warps, thread = pixel, work items (m, 16-column block) dealt to the two groups ------------------------------
+        constexpr int NCH = C::NACC / 16;
+        constexpr int ITEMS = K64_TM * NCH;                     // 12 (N = 64) or 3 (N = 16)
+        const int et = tid & 127, egrp = tid >> 7;
+        const uint32_t tl = tbase + ((uint32_t)((warp & 3) * 32) << 16);
+        const bool has_res = (p.mode == SRM_ADD_STORE_F16);
+        unsigned g = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++g) {
+            const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
+            const int y0 = ty * SR_TY, x0 = tx * K64_TX;
+            const unsigned a = g & 1;
+            sr_mbar_wait(acc_full + a, (g >> 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+#pragma unroll 1
+            for (int it0 = egrp; it0 < ITEMS; it0 += 4) {        // two items of this group per round: it0 and it0 + 2
+                uint32_t v[2][16];
+                float4 res[2][4];
+                bool ins[2]; size_t opix[2]; int c16s[2];
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const int it = it0 + 2 * u;
+                    const int m = (it < ITEMS) ? it / NCH : 0, c16 = (it < ITEMS) ? it % NCH : 0;
+                    const int py = y0 + (et >> 3), px = x0 + m * 8 + (et & 7);
+                    ins[u] = (it < ITEMS) & (py < p.H) & (px < p.W);
+                    opix[u] = (size_t)(py * p.out_s + p.out_oy) * ((size_t)p.W * p.out_s) + (size_t)(px * p.out_s + p.out_ox);
+                    c16s[u] = c16;
+                    if (has_res && ins[u]) {
+                        const float4* ad = reinterpret_cast<const float4*>(p.add_f + opix[u] * 64 + c16 * 16);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) res[u][q] = __ldg(ad + q);
+                    }
+                    if (it < ITEMS) sr_ld16(tl + (a * K64_TM + m) * C::NACC + c16 * 16, v[u]);     // warp-uniform condition
+                }
+                asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    if (!ins[u]) continue;
+                    const int c16 = c16s[u];
+                    const size_t pix = opix[u];
+                    float o[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) o[j] = __uint_as_float(v[u][j]) + sbias[c16 * 16 + j];
+                    if (p.mode == SRM_STORE_F16) {
+                        if (p.lrelu > 0.f) {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) o[j] = o[j] > 0.f ? o[j] : o[j] * p.lrelu;
+                        }
+                        __half2 h[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) h[j] = __floats2half2_rn(o[2 * j], o[2 * j + 1]);
+                        uint4* d = reinterpret_cast<uint4*>(p.dst_h + pix * p.dst_cstride + p.dst_c0 + c16 * 16);
+                        d[0] = *reinterpret_cast<uint4*>(&h[0]);
+                        d[1] = *reinterpret_cast<uint4*>(&h[4]);
+                    } else if (p.mode == SRM_ADD_STORE_F16) {
+                        __half2 h[8];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const float4 r = res[u][q];
+                            h[2 * q] = __floats2half2_rn(o[4 * q] + r.x, o[4 * q + 1] + r.y);
+                            h[2 * q + 1] = __floats2half2_rn(o[4 * q + 2] + r.z, o[4 * q + 3] + r.w);
+                        }
+                        uint4* d = reinterpret_cast<uint4*>(p.dst_h + pix * p.dst_cstride + p.dst_c0 + c16 * 16);
+                        d[0] = *reinterpret_cast<uint4*>(&h[0]);
+                        d[1] = *reinterpret_cast<uint4*>(&h[4]);
+                    } else {  // SRM_OUT_NCHW
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            if (c16 * 16 + j < p.n_valid) p.out_nchw[(size_t)(c16 * 16 + j) * p.H * p.W + pix] = o[j];
+                    }
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+            ws_arrive(acc_empty + a);
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" :: "r"(tbase), "r"((uint32_t)C::TCOLS) : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------
 // SFT layer: scale = C1s(lrelu(C0s(cond))), shift = C1h(lrelu(C0h(cond))), y = x*(scale+1)+shift
 // ---------------------------------------------------------------------------------------------
 struct SftParams {
@@ -934,12 +1132,38 @@ __global__ void pack_conv_phase_kernel(const float* __restrict__ W, unsigned cha
     *reinterpret_cast<__half*>(dst + off) = __float2half_rn(w);
 }
 
+// Weights for conv3x3_k64_kernel: plain [tap][NPAD][64] fp16 rows (the TMA copy applies the 128-byte swizzle).
+// phase < 0: the nine taps of the direct 3x3 conv; phase 0..3: the four taps of that sub-pixel phase
+// (same combination rule as pack_conv_phase_kernel).
+__global__ void pack_conv_k64_kernel(const float* __restrict__ W, __half* __restrict__ dst, int cout, int cin, int npad, int phase) {
+    const int ntaps = (phase < 0) ? 9 : 4;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)ntaps * npad * 64) return;
+    const int k = (int)(i % 64);
+    const int n = (int)((i / 64) % npad);
+    const int t = (int)(i / 64 / npad);
+    float w = 0.f;
+    if (n < cout && k < cin) {
+        if (phase < 0) {
+            w = W[((size_t)n * cin + k) * 9 + t];
+        } else {
+            const int py = phase >> 1, px = phase & 1, iy = t >> 1, ix = t & 1;
+            const int ky0 = (py == 0) ? (iy == 0 ? 0 : 1) : (iy == 0 ? 0 : 2), ky1 = (py == 0) ? (iy == 0 ? 0 : 2) : (iy == 0 ? 1 : 2);
+            const int kx0 = (px == 0) ? (ix == 0 ? 0 : 1) : (ix == 0 ? 0 : 2), kx1 = (px == 0) ? (ix == 0 ? 0 : 2) : (ix == 0 ? 1 : 2);
+            for (int ky = ky0; ky <= ky1; ++ky)
+                for (int kx = kx0; kx <= kx1; ++kx) w += W[((size_t)n * cin + k) * 9 + ky * 3 + kx];
+        }
+    }
+    dst[i] = __float2half_rn(w);
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-struct SrConv { unsigned char* wpack; float* bias; int cin_pad, cout, npad; unsigned char* wphase[4]; };
+struct SrConv { unsigned char* wpack; float* bias; int cin_pad, cout, npad; unsigned char* wphase[4];
+                __half* wk64; __half* wk64_phase[4]; };       // conv3x3_k64_kernel packs (Cin == 64 layers only)
 struct SrSft { float* w; unsigned char* blob; int cout; };
 
 struct k4_srnet {
@@ -992,6 +1216,26 @@ int make_conv_phases(k4_srnet* n, SrConv& c, const float* w, int cout, int cin, 
         int st = sr_alloc(n, (void**)&c.wphase[ph], bytes);
         if (st) return st;
         pack_conv_phase_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(w, c.wphase[ph], cout, cin, c.npad, nsl, ph >> 1, ph & 1);
+        K4_CUDA_TRY(cudaGetLastError());
+    }
+    return K4_OK;
+}
+
+// [tap][npad][64] packs for conv3x3_k64_kernel (direct 9 taps, and the 4 phases when `phases`)
+int make_conv_k64(k4_srnet* n, SrConv& c, const float* w, int cout, int cin, bool phases, cudaStream_t s) {
+    if (cin != 64 || (c.npad != 64 && c.npad != 16)) return K4_OK;
+    {
+        const long long total = 9LL * c.npad * 64;
+        int st = sr_alloc(n, (void**)&c.wk64, (size_t)total * 2);
+        if (st) return st;
+        pack_conv_k64_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(w, c.wk64, cout, cin, c.npad, -1);
+        K4_CUDA_TRY(cudaGetLastError());
+    }
+    for (int ph = 0; phases && ph < 4; ++ph) {
+        const long long total = 4LL * c.npad * 64;
+        int st = sr_alloc(n, (void**)&c.wk64_phase[ph], (size_t)total * 2);
+        if (st) return st;
+        pack_conv_k64_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(w, c.wk64_phase[ph], cout, cin, c.npad, ph);
         K4_CUDA_TRY(cudaGetLastError());
     }
     return K4_OK;
@@ -1095,6 +1339,51 @@ int launch_conv_ws(ConvParams p, cudaStream_t s) {
     return K4_OK;
 }
 
+// conv3x3_k64_kernel launch: tensor maps for the activation (channel, x, y; box 64 x 26 x 18) and the weight rows
+template <int N>
+int launch_conv_k64(ConvParams p, const __half* wrows, cudaStream_t s) {
+    using C = K64Cfg<N>;
+    static bool attr_set = false;
+    static int sms = 0;
+    k4_encode_tiled_fn enc = sr_encode_tiled();
+    if (!enc) return K4_ERR_UNSUPPORTED;
+    if (!attr_set) {
+        K4_CUDA_TRY(cudaFuncSetAttribute(conv3x3_k64_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+        int dev = 0;
+        K4_CUDA_TRY(cudaGetDevice(&dev));
+        K4_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        attr_set = true;
+    }
+    alignas(64) CUtensorMap ta, tb;
+    {
+        const cuuint64_t gdim[3] = {64, (cuuint64_t)p.W, (cuuint64_t)p.H};
+        const cuuint64_t gstr[2] = {(cuuint64_t)p.src_cstride * 2, (cuuint64_t)p.W * p.src_cstride * 2};
+        const cuuint32_t box[3] = {64, (cuuint32_t)K64_HX, (cuuint32_t)SR_HY}, es[3] = {1, 1, 1};
+        if (enc(&ta, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<__half*>(p.src + p.src_c0), gdim, gstr, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return K4_ERR_UNSUPPORTED;
+    }
+    {
+        const cuuint64_t gdim[2] = {64, (cuuint64_t)p.ntaps * N};
+        const cuuint64_t gstr[1] = {128};
+        const cuuint32_t box[2] = {64, (cuuint32_t)N}, es[2] = {1, 1};
+        if (enc(&tb, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(wrows), gdim, gstr, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return K4_ERR_UNSUPPORTED;
+    }
+    const int tiles = ((p.W + K64_TX - 1) / K64_TX) * ((p.H + SR_TY - 1) / SR_TY);
+    conv3x3_k64_kernel<N><<<(unsigned)(tiles < sms ? tiles : sms), K64_THREADS, C::SMEM, s>>>(p, ta, tb);
+    K4_CUDA_TRY(cudaGetLastError());
+    return K4_OK;
+}
+
+// The 64-input-channel layers go to conv3x3_k64_kernel; K4_CONV_K64=0 keeps them on conv3x3_ws_kernel (A/B switch).
+static bool sr_use_k64() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("K4_CONV_K64"); v = (e && e[0] == '0') ? 0 : 1; }
+    return v == 1;
+}
+
 // K4_CONV_V1=1 selects the one-tile-per-CTA kernel (kept as the A/B reference of the persistent one)
 static bool sr_use_v1() {
     static int v = -1;
@@ -1102,7 +1391,8 @@ static bool sr_use_v1() {
     return v == 1;
 }
 
-int run_conv(const SrConv& c, ConvParams p, cudaStream_t s) {
+int run_conv(const SrConv& c, ConvParams p, cudaStream_t s, const __half* wk64_override = nullptr) {
+    const __half* wk64 = wk64_override ? wk64_override : ((p.ntaps == 0 || p.ntaps == 9) ? c.wk64 : nullptr);
     if (!p.wpack) p.wpack = c.wpack;
     p.bias = c.bias; p.cin = c.cin_pad;
     if (p.ntaps == 0) {
@@ -1115,6 +1405,11 @@ int run_conv(const SrConv& c, ConvParams p, cudaStream_t s) {
         if (c.npad == 64) return launch_conv<64>(p, s);
         if (c.npad == 32) return launch_conv<32>(p, s);
         return launch_conv<16>(p, s);
+    }
+    if (sr_use_k64() && wk64 && p.cin == 64 && !p.upsample && (p.src_cstride % 8) == 0 && (p.src_c0 % 8) == 0 &&
+        (p.mode == SRM_STORE_F16 || p.mode == SRM_ADD_STORE_F16 || p.mode == SRM_OUT_NCHW)) {
+        const int st = (c.npad == 64) ? launch_conv_k64<64>(p, wk64, s) : (c.npad == 16) ? launch_conv_k64<16>(p, wk64, s) : K4_ERR_UNSUPPORTED;
+        if (st != K4_ERR_UNSUPPORTED) return st;
     }
     if (c.npad == 64) return launch_conv_ws<64>(p, s);
     if (c.npad == 32) return launch_conv_ws<32>(p, s);
@@ -1130,7 +1425,7 @@ int run_conv_up2x(const SrConv& c, ConvParams p, cudaStream_t s) {
         q.ntaps = 4;
         for (int t = 0; t < 4; ++t) { q.tap_dy[t] = (unsigned char)(py + (t >> 1)); q.tap_dx[t] = (unsigned char)(px + (t & 1)); }
         q.out_s = 2; q.out_oy = py; q.out_ox = px;
-        const int st = run_conv(c, q, s);
+        const int st = run_conv(c, q, s, c.wk64_phase[ph]);
         if (st != K4_OK) return st;
     }
     return K4_OK;
@@ -1228,11 +1523,11 @@ extern "C" int k4_srnet_create(const k4_srnet_desc* d, k4_stream_t stream, k4_sr
         SR_TRY(make_sft(n, n->rrdb_sft[i], P + k, 64, s)); k += 8;
     }
     SR_TRY(make_sft(n, n->sftbody, P + k, 64, s)); k += 8;
-    SR_TRY(make_conv(n, n->conv_body, P[k], P[k + 1], 64, 64, s)); k += 2;
-    SR_TRY(make_conv(n, n->conv_up1, P[k], P[k + 1], 64, 64, s)); SR_TRY(make_conv_phases(n, n->conv_up1, P[k], 64, 64, s)); k += 2;
-    SR_TRY(make_conv(n, n->conv_up2, P[k], P[k + 1], 64, 64, s)); SR_TRY(make_conv_phases(n, n->conv_up2, P[k], 64, 64, s)); k += 2;
-    SR_TRY(make_conv(n, n->conv_hr, P[k], P[k + 1], 64, 64, s)); k += 2;
-    SR_TRY(make_conv(n, n->conv_last, P[k], P[k + 1], 3, 64, s)); k += 2;
+    SR_TRY(make_conv(n, n->conv_body, P[k], P[k + 1], 64, 64, s)); SR_TRY(make_conv_k64(n, n->conv_body, P[k], 64, 64, false, s)); k += 2;
+    SR_TRY(make_conv(n, n->conv_up1, P[k], P[k + 1], 64, 64, s)); SR_TRY(make_conv_phases(n, n->conv_up1, P[k], 64, 64, s)); SR_TRY(make_conv_k64(n, n->conv_up1, P[k], 64, 64, true, s)); k += 2;
+    SR_TRY(make_conv(n, n->conv_up2, P[k], P[k + 1], 64, 64, s)); SR_TRY(make_conv_phases(n, n->conv_up2, P[k], 64, 64, s)); SR_TRY(make_conv_k64(n, n->conv_up2, P[k], 64, 64, true, s)); k += 2;
+    SR_TRY(make_conv(n, n->conv_hr, P[k], P[k + 1], 64, 64, s)); SR_TRY(make_conv_k64(n, n->conv_hr, P[k], 64, 64, false, s)); k += 2;
+    SR_TRY(make_conv(n, n->conv_last, P[k], P[k + 1], 3, 64, s)); SR_TRY(make_conv_k64(n, n->conv_last, P[k], 3, 64, false, s)); k += 2;
 #undef SR_TRY
     *out = n;
     return K4_OK;
