@@ -114,13 +114,16 @@ struct RayGenParams {
     float K[9];
     float c2w[12];
     int H, W, ndc, inverse_y, flip_x, flip_y;
+    const int* rows;              // optional: image row of every output row (a rank's share of the frame)
+    int n_rows;                   // output rows (== H when rows == nullptr)
 };
 
 __global__ void make_rays_kernel(const __grid_constant__ RayGenParams p, float* __restrict__ ro,
                                  float* __restrict__ rd, float* __restrict__ vd) {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= (long long)p.H * p.W) return;
-    const int y = (int)(idx / p.W), x = (int)(idx - (long long)y * p.W);
+    if (idx >= (long long)p.n_rows * p.W) return;
+    const int ly = (int)(idx / p.W), x = (int)(idx - (long long)ly * p.W);
+    const int y = p.rows ? __ldg(p.rows + ly) : ly;
     const int xs = p.flip_x ? (p.W - 1 - x) : x;
     const int ys = p.flip_y ? (p.H - 1 - y) : y;
     const float i = __fadd_rn((float)xs, 0.5f), j = __fadd_rn((float)ys, 0.5f);
@@ -393,16 +396,24 @@ extern "C" int k4_render_rays(const k4_scene* sc, const k4_render_args* a,
     return k4_launch_march(sc, rp, a->mlp_mode, s);
 }
 
-extern "C" int k4_make_rays(const float* h_K, const float* h_c2w, int32_t H, int32_t W, int32_t ndc,
-                            int32_t inverse_y, int32_t flip_x, int32_t flip_y,
-                            float* d_rays_o, float* d_rays_d, float* d_viewdirs, k4_stream_t stream) {
-    if (!h_K || !h_c2w || !d_rays_o || !d_rays_d || !d_viewdirs || H <= 0 || W <= 0) return K4_ERR_INVALID_ARG;
+extern "C" int k4_make_rays_rows(const float* h_K, const float* h_c2w, int32_t H, int32_t W, int32_t ndc,
+                                 int32_t inverse_y, int32_t flip_x, int32_t flip_y, const int32_t* d_rows, int32_t n_rows,
+                                 float* d_rays_o, float* d_rays_d, float* d_viewdirs, k4_stream_t stream) {
+    if (!h_K || !h_c2w || !d_rays_o || !d_rays_d || !d_viewdirs || H <= 0 || W <= 0 || n_rows < 0) return K4_ERR_INVALID_ARG;
+    if (n_rows == 0) return K4_OK;
     RayGenParams p;
     memcpy(p.K, h_K, sizeof(p.K));
     memcpy(p.c2w, h_c2w, sizeof(p.c2w));
     p.H = H; p.W = W; p.ndc = ndc; p.inverse_y = inverse_y; p.flip_x = flip_x; p.flip_y = flip_y;
-    const long long n = (long long)H * W;
+    p.rows = d_rows; p.n_rows = d_rows ? n_rows : H;
+    const long long n = (long long)p.n_rows * W;
     make_rays_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(p, d_rays_o, d_rays_d, d_viewdirs);
     K4_CUDA_TRY(cudaGetLastError());
     return K4_OK;
+}
+
+extern "C" int k4_make_rays(const float* h_K, const float* h_c2w, int32_t H, int32_t W, int32_t ndc,
+                            int32_t inverse_y, int32_t flip_x, int32_t flip_y,
+                            float* d_rays_o, float* d_rays_d, float* d_viewdirs, k4_stream_t stream) {
+    return k4_make_rays_rows(h_K, h_c2w, H, W, ndc, inverse_y, flip_x, flip_y, nullptr, H, d_rays_o, d_rays_d, d_viewdirs, stream);
 }

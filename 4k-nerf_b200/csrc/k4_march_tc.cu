@@ -118,12 +118,13 @@ __device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t (&v)[4]) {
 // {lo, hi} -> packed fp16x2 with ReLU applied by the conversion itself
 __device__ __forceinline__ uint32_t cvt_relu_h2(uint32_t lo_bits, uint32_t hi_bits) {
     uint32_t d;
-    asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;\n" : "=r"(d) : "f"(__uint_as_float(hi_bits)), "f"(__uint_as_float(lo_bits)));
+    asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;\n" : "=r"(d) : "f"(__uint_as_float(hi_bits)), "f"(__uint_as_float(lo_bits)));
     return d;
 }
 __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
-    __half2 h = __floats2half2_rn(lo, hi);
-    return *reinterpret_cast<uint32_t*>(&h);
+    uint32_t d;      // saturating: a feature beyond the fp16 range becomes +-65504, never inf
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;\n" : "=r"(d) : "f"(hi), "f"(lo));
+    return d;
 }
 __device__ __forceinline__ void wg_bar(int wg) { asm volatile("bar.sync %0, 128;\n" :: "r"(wg + 1) : "memory"); }
 __device__ __forceinline__ bool wg_bar_or(int wg, bool pred) {

@@ -75,6 +75,13 @@ __device__ __forceinline__ void sr_ld16(uint32_t taddr, uint32_t (&v)[16]) {
                    "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
                  : "r"(taddr));
 }
+// fp32 pair -> fp16x2, round to nearest, SATURATING (|x| > 65504 -> +-65504 instead of inf): activations of a
+// trained checkpoint may exceed the fp16 range; a clamped operand degrades gracefully, an inf poisons the frame.
+__device__ __forceinline__ __half2 sr_h2sat(float lo, float hi) {
+    uint32_t d;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;\n" : "=r"(d) : "f"(hi), "f"(lo));
+    return *reinterpret_cast<__half2*>(&d);
+}
 __device__ __forceinline__ void cp_async16(void* dst_smem, const void* src, int src_bytes) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" :: "r"(sr_s32(dst_smem)), "l"(src), "r"(src_bytes) : "memory");
 }
@@ -226,7 +233,7 @@ __global__ void __launch_bounds__(128) conv3x3_tc_kernel(const __grid_constant__
             }
             __half2 h[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) h[j] = __floats2half2_rn(o[2 * j], o[2 * j + 1]);
+            for (int j = 0; j < 8; ++j) h[j] = sr_h2sat(o[2 * j], o[2 * j + 1]);
             uint4* d = reinterpret_cast<uint4*>(p.dst_h + pix * p.dst_cstride + p.dst_c0 + c16 * 16);
             d[0] = *reinterpret_cast<uint4*>(&h[0]);
             d[1] = *reinterpret_cast<uint4*>(&h[4]);
@@ -244,8 +251,8 @@ __global__ void __launch_bounds__(128) conv3x3_tc_kernel(const __grid_constant__
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 const float4 r = a[q];
-                h[2 * q] = __floats2half2_rn(o[4 * q] + r.x, o[4 * q + 1] + r.y);
-                h[2 * q + 1] = __floats2half2_rn(o[4 * q + 2] + r.z, o[4 * q + 3] + r.w);
+                h[2 * q] = sr_h2sat(o[4 * q] + r.x, o[4 * q + 1] + r.y);
+                h[2 * q + 1] = sr_h2sat(o[4 * q + 2] + r.z, o[4 * q + 3] + r.w);
             }
             uint4* d = reinterpret_cast<uint4*>(p.dst_h + pix * p.dst_cstride + p.dst_c0 + c16 * 16);
             d[0] = *reinterpret_cast<uint4*>(&h[0]);
@@ -496,7 +503,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv3x3_ws_kernel(const __grid_
                         }
                         __half2 h[8];
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) h[j] = __floats2half2_rn(o[2 * j], o[2 * j + 1]);
+                        for (int j = 0; j < 8; ++j) h[j] = sr_h2sat(o[2 * j], o[2 * j + 1]);
                         uint4* d = reinterpret_cast<uint4*>(p.dst_h + pix * p.dst_cstride + p.dst_c0 + c16 * 16);
                         d[0] = *reinterpret_cast<uint4*>(&h[0]);
                         d[1] = *reinterpret_cast<uint4*>(&h[4]);
@@ -512,8 +519,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv3x3_ws_kernel(const __grid_
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
                             const float4 r = res[c16 * 4 + q];
-                            h[2 * q] = __floats2half2_rn(o[4 * q] + r.x, o[4 * q + 1] + r.y);
-                            h[2 * q + 1] = __floats2half2_rn(o[4 * q + 2] + r.z, o[4 * q + 3] + r.w);
+                            h[2 * q] = sr_h2sat(o[4 * q] + r.x, o[4 * q + 1] + r.y);
+                            h[2 * q + 1] = sr_h2sat(o[4 * q + 2] + r.z, o[4 * q + 3] + r.w);
                         }
                         uint4* d = reinterpret_cast<uint4*>(p.dst_h + pix * p.dst_cstride + p.dst_c0 + c16 * 16);
                         d[0] = *reinterpret_cast<uint4*>(&h[0]);
@@ -705,7 +712,7 @@ __global__ void __launch_bounds__(K64_THREADS, 1) conv3x3_k64_kernel(const __gri
                         }
                         __half2 h[8];
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) h[j] = __floats2half2_rn(o[2 * j], o[2 * j + 1]);
+                        for (int j = 0; j < 8; ++j) h[j] = sr_h2sat(o[2 * j], o[2 * j + 1]);
                         uint4* d = reinterpret_cast<uint4*>(p.dst_h + pix * p.dst_cstride + p.dst_c0 + c16 * 16);
                         d[0] = *reinterpret_cast<uint4*>(&h[0]);
                         d[1] = *reinterpret_cast<uint4*>(&h[4]);
@@ -714,8 +721,8 @@ __global__ void __launch_bounds__(K64_THREADS, 1) conv3x3_k64_kernel(const __gri
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
                             const float4 r = res[u][q];
-                            h[2 * q] = __floats2half2_rn(o[4 * q] + r.x, o[4 * q + 1] + r.y);
-                            h[2 * q + 1] = __floats2half2_rn(o[4 * q + 2] + r.z, o[4 * q + 3] + r.w);
+                            h[2 * q] = sr_h2sat(o[4 * q] + r.x, o[4 * q + 1] + r.y);
+                            h[2 * q + 1] = sr_h2sat(o[4 * q + 2] + r.z, o[4 * q + 3] + r.w);
                         }
                         uint4* d = reinterpret_cast<uint4*>(p.dst_h + pix * p.dst_cstride + p.dst_c0 + c16 * 16);
                         d[0] = *reinterpret_cast<uint4*>(&h[0]);
@@ -792,7 +799,7 @@ __global__ void __launch_bounds__(128) sft_kernel(const __grid_constant__ SftPar
         } else {
             __half2 h[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) h[j] = __floats2half2_rn(y[2 * j], y[2 * j + 1]);
+            for (int j = 0; j < 4; ++j) h[j] = sr_h2sat(y[2 * j], y[2 * j + 1]);
             *reinterpret_cast<uint4*>(p.dst_h + pix * p.dst_cstride + p.dst_c0 + o0) = *reinterpret_cast<uint4*>(h);
         }
     }
@@ -899,7 +906,7 @@ __global__ void __launch_bounds__(128, (COUT == 64) ? 2 : 4) sft_tc_kernel(const
 #pragma unroll
         for (int kc = 0; kc < 4; ++kc) {
             const float4 a = cnd[2 * kc], b = cnd[2 * kc + 1];
-            __half2 h[4] = {__floats2half2_rn(a.x, a.y), __floats2half2_rn(a.z, a.w), __floats2half2_rn(b.x, b.y), __floats2half2_rn(b.z, b.w)};
+            __half2 h[4] = {sr_h2sat(a.x, a.y), sr_h2sat(a.z, a.w), sr_h2sat(b.x, b.y), sr_h2sat(b.z, b.w)};
             *reinterpret_cast<uint4*>(atile + tc_canon_off(tid, kc, 4)) = *reinterpret_cast<uint4*>(h);
         }
         uint4 xraw[COUT / 4];                                   // the x row: COUT fp32 (all of it) or COUT fp16 (first half)
@@ -936,7 +943,7 @@ __global__ void __launch_bounds__(128, (COUT == 64) ? 2 : 4) sft_tc_kernel(const
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
                 const float a = __uint_as_float(v[2 * j]), b = __uint_as_float(v[2 * j + 1]);
-                const __half2 hh = __floats2half2_rn(fmaxf(a, 0.2f * a), fmaxf(b, 0.2f * b));
+                const __half2 hh = sr_h2sat(fmaxf(a, 0.2f * a), fmaxf(b, 0.2f * b));
                 h[j] = *reinterpret_cast<const uint32_t*>(&hh);
             }
             sr_st16(tl + D0 + c * 16, h);
@@ -992,7 +999,7 @@ __global__ void __launch_bounds__(128, (COUT == 64) ? 2 : 4) sft_tc_kernel(const
             } else {
                 __half2 h[8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) h[j] = __floats2half2_rn(y[2 * j], y[2 * j + 1]);
+                for (int j = 0; j < 8; ++j) h[j] = sr_h2sat(y[2 * j], y[2 * j + 1]);
                 uint4* d = reinterpret_cast<uint4*>(p.dst_h + pix * p.dst_cstride + p.dst_c0 + c16 * 16);
                 d[0] = *reinterpret_cast<uint4*>(&h[0]);
                 d[1] = *reinterpret_cast<uint4*>(&h[4]);

@@ -32,6 +32,35 @@ def _fp(tensors):
     return tuple((t.data_ptr(), t._version, tuple(t.shape)) for t in tensors if t is not None)
 
 
+def cached_host(module, name, tensors, fn):
+    """Host copies of small device buffers (act_shift, scene centre ...) cached by the buffers'
+    (data_ptr, _version): float(buffer) is a device->host copy + stream sync, which must not happen on
+    every render call."""
+    cache = module.__dict__.setdefault('_k4_hostcache', {})
+    fp = _fp(tensors)
+    e = cache.get(name)
+    if e is None or e[0] != fp:
+        e = (fp, fn())
+        cache[name] = e
+    return e[1]
+
+
+def host_float(module, name):
+    """float(module.<name>) without a per-call device sync when the attribute is a CUDA tensor (voxel_size /
+    voxel_size_ratio become CUDA tensors once _set_grid_resolution runs after .to(device))."""
+    v = getattr(module, name)
+    if torch.is_tensor(v) and v.is_cuda:
+        return cached_host(module, 'f:' + name, [v], lambda: float(v))
+    return float(v)
+
+
+def scalar_fingerprint(module, extra):
+    """Scalars baked into the device scene (k4_scene_desc): a change must rebuild it."""
+    return (float(module.fast_color_thres), host_float(module, 'voxel_size_ratio'), float(extra.get('act_shift', 0.0)),
+            float(extra.get('voxel_size', 0.0)), int(extra.get('viewbase_pe', 0)), int(extra.get('spatial_pe', 0)),
+            bool(extra.get('rgbnet_direct', True)))
+
+
 def require_cuda(*tensors):
     for t in tensors:
         if not t.is_cuda:
@@ -65,7 +94,7 @@ def build_scene(kind, module, extra):
     mc = module.mask_cache
     layers = linear_layers(module.rgbnet)
     require_cuda(density, k0, mc.mask)
-    fingerprint = _fp(gather_tensors(module, extra))
+    fingerprint = (_fp(gather_tensors(module, extra)), scalar_fingerprint(module, extra))
     dev = density.device
     d = _lib.SceneDesc()
     d.kind = kind
@@ -79,7 +108,7 @@ def build_scene(kind, module, extra):
     d.xyz2ijk_shift[:] = mc.xyz2ijk_shift.detach().cpu().tolist()
     d.act_shift = float(extra.get('act_shift', 0.0))
     d.voxel_size = float(extra.get('voxel_size', 0.0))
-    d.voxel_size_ratio = float(module.voxel_size_ratio)
+    d.voxel_size_ratio = host_float(module, 'voxel_size_ratio')
     d.fast_color_thres = float(module.fast_color_thres)
     d.max_world_size = int(max(X, Y, Z))
     d.mpi_depth = int(extra.get('mpi_depth', 0))
@@ -130,7 +159,7 @@ class FusedRenderMixin:
     def _get_scene(self):
         h = getattr(self, '_k4_handle', None)
         extra = self._scene_extra()
-        if h is not None and _fp(gather_tensors(self, extra)) == h.fingerprint:
+        if h is not None and (_fp(gather_tensors(self, extra)), scalar_fingerprint(self, extra)) == h.fingerprint:
             return h
         h = build_scene(self._k4_kind, self, extra)
         object.__setattr__(self, '_k4_handle', h)
@@ -162,8 +191,10 @@ class FusedRenderMixin:
 
     @torch.no_grad()
     def render_rays(self, rays_o, rays_d, viewdirs, render_kwargs, image_hw=None, mlp_mode=None,
-                    debug=False):
-        """Run the fused kernel.  Returns dict(rgb_marched, alphainv_last[, depth][, ray_stats, t_minmax, counters])."""
+                    debug=False, out=None):
+        """Run the fused kernel.  Returns dict(rgb_marched, alphainv_last[, depth][, ray_stats, t_minmax, counters]).
+        ``out``: optional dict of caller-owned contiguous fp32 CUDA tensors ``rgb_marched [N,3]``, ``alphainv_last [N]``
+        (and ``depth [N]``) the kernel writes into -- e.g. views of a packed communication buffer (k4nerf.dist)."""
         assert rays_o.dim() == 2 and rays_o.shape[-1] == 3, 'Only suuport point queries in [N, 3] format'
         require_cuda(rays_o, rays_d, viewdirs)
         h = self._get_scene()
@@ -172,10 +203,17 @@ class FusedRenderMixin:
         rays_d = rays_d.to(torch.float32).contiguous()
         viewdirs = viewdirs.to(torch.float32).contiguous()
         N = rays_o.shape[0]
-        rgb = torch.empty((N, 3), device=dev, dtype=torch.float32)
-        alphainv = torch.empty((N,), device=dev, dtype=torch.float32)
         want_depth = bool(render_kwargs.get('render_depth', False))
-        depth = torch.empty((N,), device=dev, dtype=torch.float32) if want_depth else None
+        if out is not None:
+            rgb, alphainv, depth = out['rgb_marched'], out['alphainv_last'], (out.get('depth') if want_depth else None)
+            for t, shp in ((rgb, (N, 3)), (alphainv, (N,)), (depth, (N,))):
+                if t is not None and not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and tuple(t.shape) == shp):
+                    raise ValueError('render_rays(out=...): outputs must be contiguous fp32 CUDA tensors of shape [N,3] / [N]')
+            want_depth = depth is not None
+        else:
+            rgb = torch.empty((N, 3), device=dev, dtype=torch.float32)
+            alphainv = torch.empty((N,), device=dev, dtype=torch.float32)
+            depth = torch.empty((N,), device=dev, dtype=torch.float32) if want_depth else None
         a = _lib.RenderArgs()
         a.near_ = float(render_kwargs['near'])
         a.far_ = float(render_kwargs['far'])

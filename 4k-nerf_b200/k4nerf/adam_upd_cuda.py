@@ -13,10 +13,18 @@ def _check(param, grad, exp_avg, exp_avg_sq, *more):
             raise RuntimeError('adam update expects float32 tensors of one size')
 
 
+def _bump(*tensors):
+    """The kernels write through raw pointers: tell autograd / the device-scene fingerprint
+    (k4nerf._scene._fp uses tensor._version) that the tensors changed in place."""
+    for t in tensors:
+        torch.autograd.graph.increment_version(t)
+
+
 def adam_upd(param, grad, exp_avg, exp_avg_sq, step, beta1, beta2, lr, eps):
     _check(param, grad, exp_avg, exp_avg_sq)
     _call('k4_op_adam_upd', _p(param), _p(grad), _p(exp_avg), _p(exp_avg_sq), None, param.numel(), int(step),
           float(beta1), float(beta2), float(lr), float(eps), 0, _s(param))
+    _bump(param, exp_avg, exp_avg_sq)
 
 
 def masked_adam_upd(param, grad, exp_avg, exp_avg_sq, step, beta1, beta2, lr, eps):
@@ -24,12 +32,14 @@ def masked_adam_upd(param, grad, exp_avg, exp_avg_sq, step, beta1, beta2, lr, ep
     _check(param, grad, exp_avg, exp_avg_sq)
     _call('k4_op_adam_upd', _p(param), _p(grad), _p(exp_avg), _p(exp_avg_sq), None, param.numel(), int(step),
           float(beta1), float(beta2), float(lr), float(eps), 1, _s(param))
+    _bump(param, exp_avg, exp_avg_sq)
 
 
 def adam_upd_with_perlr(param, grad, exp_avg, exp_avg_sq, perlr, step, beta1, beta2, lr, eps):
     _check(param, grad, exp_avg, exp_avg_sq, perlr)
     _call('k4_op_adam_upd', _p(param), _p(grad), _p(exp_avg), _p(exp_avg_sq), _p(perlr), param.numel(), int(step),
           float(beta1), float(beta2), float(lr), float(eps), 0, _s(param))
+    _bump(param, exp_avg, exp_avg_sq)
 
 
 __all__ = ['adam_upd', 'masked_adam_upd', 'adam_upd_with_perlr']

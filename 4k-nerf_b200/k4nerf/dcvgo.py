@@ -7,7 +7,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib, grid
-from ._scene import FusedRenderMixin
+from ._scene import FusedRenderMixin, cached_host, host_float
 from .maintain import GridMaintenanceMixin
 
 
@@ -105,7 +105,20 @@ class DirectContractedVoxGO(FusedRenderMixin, GridMaintenanceMixin, nn.Module):
         if key in state_dict and state_dict[key].shape != self.mask_cache.mask.shape:
             self.mask_cache.mask = torch.zeros_like(state_dict[key])
         super()._load_from_state_dict(state_dict, prefix, *args, **kwargs)
+        self.world_size = torch.tensor(list(self.density.grid.shape[2:]), dtype=torch.long)
+        self.world_len = int(self.world_size[0])
         self.invalidate_scene()
+
+    def forward(self, rays_o, rays_d, viewdirs, global_step=None, is_train=False, **render_kwargs):
+        """lib/dcvgo.py:262-382.  The dict-valued fast_color_thres schedule (lib/dcvgo.py:269-271) is applied
+        here; the threshold is baked into the device scene, whose fingerprint sees the change."""
+        if isinstance(self._fast_color_thres, dict) and global_step in self._fast_color_thres:
+            print(f'dcvgo: update fast_color_thres {self.fast_color_thres} => {self._fast_color_thres[global_step]}')
+            self.fast_color_thres = self._fast_color_thres[global_step]
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            from .train_forward import forward_samples
+            return forward_samples(self, rays_o, rays_d, viewdirs, global_step=global_step, is_train=is_train, **render_kwargs)
+        return super().forward(rays_o, rays_d, viewdirs, global_step=global_step, **render_kwargs)
 
     def resolve_mlp_mode(self, mode):
         if mode == 'tc':
@@ -113,10 +126,13 @@ class DirectContractedVoxGO(FusedRenderMixin, GridMaintenanceMixin, nn.Module):
         return super().resolve_mlp_mode(mode)
 
     def _scene_extra(self):
+        bufs = [self.act_shift, self.scene_center, self.scene_radius]
+        act, center, radius = cached_host(self, 'scene_host', bufs, lambda: (
+            float(self.act_shift), self.scene_center.detach().cpu().tolist(), self.scene_radius.detach().cpu().tolist()))
         return {
-            'act_shift': float(self.act_shift), 'voxel_size': float(self.voxel_size), 'rgbnet_direct': True,
+            'act_shift': act, 'voxel_size': host_float(self, 'voxel_size'), 'rgbnet_direct': True,
             'viewbase_pe': self.viewbase_pe if self.rgbnet is not None else 0,
-            'scene_center': self.scene_center.detach().cpu().tolist(), 'scene_radius': self.scene_radius.detach().cpu().tolist(),
+            'scene_center': center, 'scene_radius': radius,
             'bg_len': float(self.bg_len), 'world_len': int(self.world_len),
         }
 

@@ -35,21 +35,28 @@ def cyclic_pad_rows(H, world_size, block=ROW_BLOCK):
 
 
 def unpack_frame_cyclic(gathered, H, W, world_size, block=ROW_BLOCK):
-    """[world, 5 * n_pad] (block-cyclic bands) -> dict of full-frame tensors in image order."""
+    """[world, 5 * n_pad] (block-cyclic bands) -> dict of full-frame tensors in image order.
+    Image block b sits at local block b // world of rank b % world, so image order is the (local block,
+    rank) transpose of the gathered buffer: one strided copy per quantity, no index kernels."""
     rows_pad = cyclic_pad_rows(H, world_size, block)
     n_pad = rows_pad * W
+    nlb = rows_pad // block
     g = gathered.view(world_size, 5 * n_pad)
-    dev = gathered.device
-    rgb = torch.empty(H, W, 3, device=dev, dtype=gathered.dtype)
-    depth = torch.empty(H, W, device=dev, dtype=gathered.dtype)
-    ainv = torch.empty(H, W, device=dev, dtype=gathered.dtype)
-    for r in range(world_size):
-        rows = cyclic_rows(H, r, world_size, block).to(dev)
-        k = rows.numel()
-        rgb[rows] = g[r, :3 * n_pad].view(rows_pad, W, 3)[:k]
-        depth[rows] = g[r, 3 * n_pad:4 * n_pad].view(rows_pad, W)[:k]
-        ainv[rows] = g[r, 4 * n_pad:5 * n_pad].view(rows_pad, W)[:k]
-    return {'rgb_marched': rgb.reshape(H * W, 3), 'depth': depth.reshape(H * W), 'alphainv_last': ainv.reshape(H * W)}
+
+    def image_order(x, c):          # x: [world, rows_pad * W * c]
+        return x.reshape(world_size, nlb, block * W * c).transpose(0, 1).reshape(-1)[:H * W * c]
+    rgb = image_order(g[:, :3 * n_pad], 3).view(H * W, 3)
+    depth = image_order(g[:, 3 * n_pad:4 * n_pad], 1)
+    ainv = image_order(g[:, 4 * n_pad:5 * n_pad], 1)
+    return {'rgb_marched': rgb, 'depth': depth, 'alphainv_last': ainv}
+
+
+def packed_band_views(buf, n_band_rays, n_pad_rays):
+    """Views of a ``[5 * n_pad]`` packed band buffer (layout of :func:`pack_band`) that the marcher can write
+    into directly (``render_rays(out=...)``): no pack copies.  The caller zero-fills the pad once at allocation."""
+    return {'rgb_marched': buf[0:3 * n_band_rays].view(n_band_rays, 3),
+            'depth': buf[3 * n_pad_rays:3 * n_pad_rays + n_band_rays],
+            'alphainv_last': buf[4 * n_pad_rays:4 * n_pad_rays + n_band_rays]}
 
 
 def band_rows(H, world_size):
@@ -87,12 +94,44 @@ def unpack_frame(gathered, H, W, world_size):
     return {'rgb_marched': rgb.reshape(H * W, 3), 'depth': depth.reshape(H * W), 'alphainv_last': ainv.reshape(H * W)}
 
 
+class CyclicFrame:
+    """Cached plan + buffers of one rank for block-cyclic frame rendering (H x W over `world` ranks): the
+    rank's row list on the device, its packed send buffer (pad zeroed once) with output views for the
+    marcher, and the gather buffer.  ``render(make_rays, render_fn)`` = rays of the rank's rows only
+    (``make_rays(rows) -> ro, rd, vd`` each [k*W,3]) -> fused march straight into the packed buffer ->
+    ONE all-gather -> image-order transpose."""
+
+    def __init__(self, H, W, device, group=None):
+        self.H, self.W, self.group = H, W, group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.rows = cyclic_rows(H, self.rank, self.world).to(device=device, dtype=torch.int32).contiguous()
+        self.k = int(self.rows.numel())
+        self.n_band = self.k * W
+        self.n_pad = cyclic_pad_rows(H, self.world) * W
+        self.buf = torch.zeros(5 * self.n_pad, device=device, dtype=torch.float32)
+        self.out = packed_band_views(self.buf, self.n_band, self.n_pad)
+        self.gathered = torch.empty(self.world * 5 * self.n_pad, device=device, dtype=torch.float32) if self.world > 1 else self.buf
+
+    def gather(self):
+        if self.world > 1:
+            dist.all_gather_into_tensor(self.gathered, self.buf, group=self.group)
+        return unpack_frame_cyclic(self.gathered, self.H, self.W, self.world)
+
+    def render(self, make_rays, render_fn):
+        if self.k > 0:
+            ro, rd, vd = make_rays(self.rows)
+            render_fn(ro, rd, vd, (self.k, self.W), self.out)
+        return self.gather()
+
+
 def render_frame_sharded(render_fn, rays_o, rays_d, viewdirs, H, W, group=None, gather=True, layout='cyclic'):
     """Render this rank's rows with ``render_fn(ro, rd, vd, image_hw) -> dict`` and all-gather the
     packed bands.  ``rays_*`` are the FULL frame ``[H*W, 3]`` (replicated or generated per rank); only
     this rank's rows are read.  ``layout``: 'cyclic' (8-row blocks dealt round-robin, load balanced,
     default) or 'bands' (contiguous).  Returns the full-frame dict on every rank (``gather=True``) or
-    this rank's band dict."""
+    this rank's band dict.  (The device-resident drivers use :class:`CyclicFrame`, which generates only
+    the rank's rays and lets the kernel write into the packed buffer.)"""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     if layout == 'cyclic' and world > 1:

@@ -5,7 +5,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib, grid
-from ._scene import FusedRenderMixin
+from ._scene import FusedRenderMixin, cached_host, host_float
 from .maintain import GridMaintenanceMixin
 
 
@@ -112,30 +112,46 @@ class DirectVoxGO(FusedRenderMixin, GridMaintenanceMixin, nn.Module):
         if key in state_dict and state_dict[key].shape != self.mask_cache.mask.shape:
             self.mask_cache.mask = torch.zeros_like(state_dict[key])
         super()._load_from_state_dict(state_dict, prefix, *args, **kwargs)
+        # the constructor arithmetic may be off by one voxel from the checkpoint (fp32 cube root):
+        # keep world_size / max_world_size (depth normalisation, TV weights, scale_volume_grid) consistent with the grids
+        self.world_size = torch.tensor(list(self.density.grid.shape[2:]), dtype=torch.long)
+        self.max_world_size = self.world_size.max()
         self.invalidate_scene()
 
     def _scene_extra(self):
         return {
-            'act_shift': float(self.act_shift), 'voxel_size': float(self.voxel_size),
+            'act_shift': cached_host(self, 'act_shift', [self.act_shift], lambda: float(self.act_shift)),
+            'voxel_size': host_float(self, 'voxel_size'),
             'rgbnet_direct': self.rgbnet_direct, 'viewbase_pe': self.viewbase_pe if self.rgbnet is not None else 0,
         }
 
 
 # --- ray helpers with the reference names (lib/dvgo.py:516-582); generated on the device -------------
-def get_rays_of_a_view(H, W, K, c2w, ndc, inverse_y, flip_x, flip_y, mode='center'):
-    """Pixel-centre rays of one view, ``[H, W, 3]`` each, produced by ``k4_make_rays``."""
+def get_rays_of_a_view(H, W, K, c2w, ndc, inverse_y, flip_x, flip_y, mode='center', rows=None, device=None):
+    """Pixel-centre rays of one view, ``[H, W, 3]`` each, produced by ``k4_make_rays``.
+    ``rows`` (int32 CUDA tensor of image-row indices, not in the reference signature): only those rows are
+    generated, ``[len(rows), W, 3]`` -- a rank's share of the frame in the multi-GPU driver."""
     if mode != 'center':
         raise NotImplementedError("only mode='center' (the render path) is built")
     import ctypes as C
     c2w = torch.as_tensor(c2w, dtype=torch.float32)
-    dev = c2w.device if c2w.is_cuda else torch.device('cuda', torch.cuda.current_device())
+    if device is not None:
+        dev = torch.device(device)
+    elif rows is not None:
+        dev = rows.device
+    else:
+        dev = c2w.device if c2w.is_cuda else torch.device('cuda', torch.cuda.current_device())
     Kh = (C.c_float * 9)(*np.asarray(K, dtype=np.float32).reshape(-1)[:9].tolist())
     ch = (C.c_float * 12)(*c2w.detach().cpu().reshape(-1)[:12].tolist())
     H, W = int(H), int(W)
-    out = [torch.empty((H, W, 3), device=dev, dtype=torch.float32) for _ in range(3)]
+    n_rows = H if rows is None else int(rows.numel())
+    if rows is not None:
+        assert rows.is_cuda and rows.dtype == torch.int32 and rows.is_contiguous()
+    out = [torch.empty((n_rows, W, 3), device=dev, dtype=torch.float32) for _ in range(3)]
     with torch.cuda.device(dev):
         stream = torch.cuda.current_stream(dev).cuda_stream
-        _lib.check(_lib.lib.k4_make_rays(Kh, ch, H, W, int(bool(ndc)), int(bool(inverse_y)), int(bool(flip_x)),
-                                         int(bool(flip_y)), out[0].data_ptr(), out[1].data_ptr(),
-                                         out[2].data_ptr(), C.c_void_p(stream)), 'k4_make_rays')
+        _lib.check(_lib.lib.k4_make_rays_rows(Kh, ch, H, W, int(bool(ndc)), int(bool(inverse_y)), int(bool(flip_x)),
+                                              int(bool(flip_y)), rows.data_ptr() if rows is not None else None, n_rows,
+                                              out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(),
+                                              C.c_void_p(stream)), 'k4_make_rays_rows')
     return out[0], out[1], out[2]

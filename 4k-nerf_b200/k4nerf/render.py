@@ -138,13 +138,19 @@ def render_frame_4k_sharded(model, net_sr, H, W, K, c2w, ndc, render_kwargs, tes
     reference tiles / tile row-parts (one all-gather of the x4 blocks).  Every rank returns the full
     frame; values are identical to the single-GPU :func:`render_frame_4k`."""
     from . import dist as kdist
-    rays_o, rays_d, viewdirs = dvgo.get_rays_of_a_view(
-        H, W, K, torch.as_tensor(np.asarray(c2w), dtype=torch.float32), ndc,
-        inverse_y=render_kwargs['inverse_y'], flip_x=flip_x, flip_y=flip_y)
     kw = dict(render_kwargs)
     kw['render_depth'] = True
-    fn = lambda ro, rd, vd, hw: model.render_rays(ro.contiguous(), rd.contiguous(), vd.contiguous(), kw, image_hw=hw)
-    lr = kdist.render_frame_sharded(fn, rays_o.view(-1, 3), rays_d.view(-1, 3), viewdirs.view(-1, 3), H, W, group=group)
+    dev = next(model.parameters()).device
+    cache = model.__dict__.setdefault('_k4_cyclic_frames', {})
+    key = (H, W, dev, id(group))
+    frame = cache.get(key)
+    if frame is None:
+        frame = cache[key] = kdist.CyclicFrame(H, W, dev, group)
+    c2w_t = torch.as_tensor(np.asarray(c2w), dtype=torch.float32)
+    make = lambda rows: tuple(t.view(-1, 3) for t in dvgo.get_rays_of_a_view(
+        H, W, K, c2w_t, ndc, inverse_y=render_kwargs['inverse_y'], flip_x=flip_x, flip_y=flip_y, rows=rows, device=dev))
+    fn = lambda ro, rd, vd, hw, out: model.render_rays(ro, rd, vd, kw, image_hw=hw, out=out)
+    lr = frame.render(make, fn)          # rank's rays only -> fused march into the packed buffer -> one all-gather -> transpose
     x = lr['rgb_marched'].view(H, W, 3).permute(2, 0, 1).unsqueeze(0).contiguous()
     cond = lr['depth'].view(1, H, W).contiguous()
     sr = net_sr.tile_process_sharded(x, cond, tile_size=test_tile if test_tile else max(H, W), group=group)

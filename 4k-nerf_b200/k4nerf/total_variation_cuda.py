@@ -16,6 +16,7 @@ def total_variation_add_grad(param, grad, wx, wy, wz, dense_mode):
         raise RuntimeError('total_variation_add_grad expects float32 [1,C,I,J,K] param and grad of the same shape')
     _call('k4_op_total_variation_add_grad', _p(param), _p(grad), float(wx), float(wy), float(wz), int(bool(dense_mode)),
           param.numel(), int(param.shape[2]), int(param.shape[3]), int(param.shape[4]), _s(param))
+    torch.autograd.graph.increment_version(grad)        # written through a raw pointer
 
 
 __all__ = ['total_variation_add_grad']

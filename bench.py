@@ -142,6 +142,16 @@ def hbm_peak():
     return HBM_FALLBACK_GBS, 'fallback (B200_PROFILING.md 6.65 TB/s)'
 
 
+def tensor_peak():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))['bf16_tflops_sustained']), 'measured (MEASURED_PEAKS.json bf16_tflops_sustained)'
+        except Exception:
+            pass
+    return 1400.0, 'fallback (B200_PROFILING.md: ~1.4 PFLOP/s sustained)'
+
+
 def algorithmic_bytes(n_rays, S_m, S_d, S_c, C=12):
     """B = 68 N + S_m + 32 S_d + 32 C S_c (fp32 grids, no reuse credit)."""
     return 68 * n_rays + S_m + 32 * S_d + 32 * C * S_c
@@ -174,16 +184,28 @@ def cpu_time_step(st, chunks):
     return n, time.perf_counter() - t0
 
 
+def cpu_threads():
+    """Threads of the CPU arm.  One pool size for torch's intra-op pool AND the C oracle's OpenMP team
+    (oracle/ops.set_num_threads): the arm's ops are a few MB each, so more than ~32 threads only adds
+    fork/join and cache-line traffic -- 128 torch x 128 OpenMP threads made the round-1 number swing 4x
+    between boxes."""
+    return max(1, min(32, os.cpu_count() or 1))
+
+
 def run_reference_arm(args, rank):
     """`--impl reference`: rank 0 alone runs; the other ranks exit 0 without work."""
     if rank != 0:
         return
     from oracle import ops
-    cores = os.cpu_count() or 1
+    cores = cpu_threads()
     ops.set_num_threads(cores)
+    try:
+        torch.set_num_interop_threads(1)
+    except RuntimeError:
+        pass
     st, _ = build_scene(args.regime)
-    n_chunks = 2
-    for w in range(min(args.warmup, 1)):
+    n_chunks = 1
+    for w in range(args.warmup):
         cpu_time_step(st, cpu_sample_rays(H4K, W4K, POSES[w % len(POSES)], n_chunks))
     tot_n, tot_t = 0, 0.0
     for k in range(args.steps):
@@ -192,11 +214,12 @@ def run_reference_arm(args, rank):
     v = tot_n / tot_t
     line = {
         'impl': 'reference', 'metric': 'rays_per_s', 'value': v, 'unit': 'rays/s', 'n_gpus': args.gpus,
-        'steps': args.steps, 'warmup': min(args.warmup, 1), 'ms_per_step': 1e3 * tot_t / max(args.steps, 1),
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * tot_t / max(args.steps, 1),
         'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
         'config': workload_config(args, 1),
         'cpu_baseline': {'value': v, 'unit': 'rays/s', 'cores': cores, 'kind': 'port',
-                         'sample': f'{n_chunks} x 8192-ray chunks of the 4032x3024 frame per step (oracle/pipeline.py on torch-CPU + C, {cores} threads)'},
+                         'sample': f'{n_chunks} x 8192-ray chunk of the 4032x3024 frame per step (oracle/pipeline.py on torch-CPU + C, '
+                                   f'{cores} threads of {os.cpu_count()} logical cores)'},
         'e2e': {'value': v, 'unit': 'rays/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
         'note': 'the reference ships no CPU path for this op chain; this is the oracle port of it on the host cores',
@@ -245,29 +268,27 @@ def main():
     kw = dict(near=2.0, far=6.0, bg=1, stepsize=0.5, inverse_y=False, flip_x=False, flip_y=False, render_depth=True)
 
     # inputs resident in HBM before the timed region: one ray set per pose, this rank's rows only
-    # (8-row blocks dealt round-robin over the ranks: every rank gets the same mix of long and short rays)
+    # (8-row blocks dealt round-robin over the ranks: every rank gets the same mix of long and short rays;
+    # only the rank's rows are generated -- k4_make_rays_rows)
     H, W = H4K, W4K
-    rows = kdist.cyclic_rows(H, rank, world).to(dev) if world > 1 else torch.arange(H, device=dev)
-    n_rows = int(rows.numel())
+    frame = kdist.CyclicFrame(H, W, dev)              # row list, packed send buffer (marcher output views), gather buffer
+    n_rows = frame.k
     r0, r1 = 0, n_rows                                   # local image = this rank's rows, in order
+    from oracle import scenes as _scenes
     bands = []
     for pose in POSES:
-        ro, rd, vd = frame_rays_device(H, W, pose, dev)
-        sel = (lambda t: t.view(H, W, 3)[rows].reshape(-1, 3).contiguous()) if world > 1 else (lambda t: t)
-        bands.append((sel(ro), sel(rd), sel(vd)))
-        del ro, rd, vd
-    torch.cuda.empty_cache()
+        K, c2w = _scenes.blender_camera(H, W, theta=pose[0], phi=pose[1])
+        ro, rd, vd = k4nerf.get_rays_of_a_view(H, W, K, c2w, False, False, False, False,
+                                               rows=frame.rows if world > 1 else None, device=dev)
+        bands.append((ro.view(-1, 3), rd.view(-1, 3), vd.view(-1, 3)))
     n_band = n_rows * W
-    n_pad = (kdist.cyclic_pad_rows(H, world) if world > 1 else H) * W
-    gathered = torch.empty(world * 5 * n_pad, device=dev, dtype=torch.float32) if world > 1 else None
 
     def step(i):
+        """One step = one fused launch over this rank's rows (written straight into the packed buffer) and, for
+        N > 1, ONE all-gather + the image-order transpose: every rank ends the step holding the whole frame."""
         ro, rd, vd = bands[i % len(bands)]
-        out = model.render_rays(ro, rd, vd, kw, image_hw=(r1 - r0, W), mlp_mode=mode)
-        if world > 1:
-            buf = kdist.pack_band(out, n_band, n_pad)
-            dist.all_gather_into_tensor(gathered, buf)
-        return out
+        model.render_rays(ro, rd, vd, kw, image_hw=(r1 - r0, W), mlp_mode=mode, out=frame.out)
+        return frame.gather() if world > 1 else frame.out
 
     def barrier():
         if world > 1:
@@ -298,11 +319,10 @@ def main():
     for i in range(args.steps):
         ro, rd, vd = bands[i % len(bands)]
         k_events[i][0].record()
-        out = model.render_rays(ro, rd, vd, kw, image_hw=(r1 - r0, W), mlp_mode=mode)
+        model.render_rays(ro, rd, vd, kw, image_hw=(r1 - r0, W), mlp_mode=mode, out=frame.out)
         k_events[i][1].record()
         if world > 1:
-            buf = kdist.pack_band(out, n_band, n_pad)
-            dist.all_gather_into_tensor(gathered, buf)
+            full = frame.gather()                        # all-gather + transpose into image order
     e1.record()
     barrier()
     t_wall1 = time.time()
@@ -324,14 +344,18 @@ def main():
     hb = [tuple(x.cpu().pin_memory() for x in bands[i]) for i in range(min(2, len(bands)))]
     h_out = torch.empty(5 * n_band, dtype=torch.float32).pin_memory()
 
+    e2e_buf = torch.zeros(5 * n_band, device=dev, dtype=torch.float32)
+    e2e_out = kdist.packed_band_views(e2e_buf, n_band, n_band)
+
     def e2e_step(i):
         ro, rd, vd = [x.to(dev, non_blocking=True) for x in hb[i % len(hb)]]
-        out = model.render_rays(ro, rd, vd, kw, image_hw=(r1 - r0, W), mlp_mode=mode)
-        buf = kdist.pack_band(out, n_band, n_band)
+        model.render_rays(ro, rd, vd, kw, image_hw=(r1 - r0, W), mlp_mode=mode, out=e2e_out)
         if world > 1:
-            bufp = kdist.pack_band(out, n_band, n_pad)
-            dist.all_gather_into_tensor(gathered, bufp)
-        h_out.copy_(buf, non_blocking=True)
+            frame.buf[:3 * n_band].copy_(e2e_buf[:3 * n_band])
+            frame.buf[3 * frame.n_pad:3 * frame.n_pad + n_band].copy_(e2e_buf[3 * n_band:4 * n_band])
+            frame.buf[4 * frame.n_pad:4 * frame.n_pad + n_band].copy_(e2e_buf[4 * n_band:])
+            frame.gather()
+        h_out.copy_(e2e_buf, non_blocking=True)
 
     e2e_steps = max(2, min(args.steps, 3))
     e2e_step(0)
@@ -348,7 +372,7 @@ def main():
     e2e = {'value': (H * W) / (e2e_ms * 1e-3), 'unit': 'rays/s',
            'h2d_bytes_per_step': int(3 * 12 * H * W), 'd2h_bytes_per_step': int(20 * H * W),
            'ms_per_step': e2e_ms, 'api': 'DirectVoxGO.render_rays on pinned host ray buffers, packed result copied back to pinned host memory'}
-    del hb
+    del hb, e2e_buf, e2e_out
 
     # ---- secondary measurements (rank 0 semantics, all ranks participate where collective) ----
     extra = {}
@@ -361,13 +385,20 @@ def main():
         peak, peak_src = hbm_peak()
         alg_bytes = algorithmic_bytes(H * W, S_m, S_d, S_c)      # whole frame (all ranks)
         achieved = alg_bytes / world / (kernel_ms * 1e-3) / 1e9   # per-launch bytes / per-launch time, GB/s
-        traffic = None
+        kernel_name = {'tc': 'k4_march_tc_kernel', 'ws': 'k4_march_ws_kernel'}.get(mode, 'k4_march_kernel')
+        traffic, ncu_pct = None, {}
         tp = os.path.join(ROOT, 'profiles', 'traffic.json')
-        if os.path.exists(tp):
+        if os.path.exists(tp) and world == 1:
             try:
-                traffic = json.load(open(tp)).get('k4_march_kernel_bytes_per_launch')
+                tj = json.load(open(tp))
+                traffic = tj.get(f'{kernel_name}_4032x3024_{args.regime}_dram_bytes_per_launch')   # ncu dram__bytes_read+write.sum of THIS launch
+                ncu_pct = tj.get(f'{kernel_name}_ncu_pct', {})
             except Exception:
                 traffic = None
+        # the resource that actually binds the FOG launch: the rgbnet contraction on the tensor pipe
+        mlp_mac = 39 * 128 + 128 * 128 + 128 * 3                  # 21,760 MAC / shaded sample
+        tp_peak, tp_src = tensor_peak()
+        mlp_tflops = 2.0 * mlp_mac * (S_c / world) / (kernel_ms * 1e-3) / 1e12
         line = {
             'metric': 'rays_per_s', 'value': value, 'unit': 'rays/s', 'n_gpus': world, 'steps': args.steps,
             'warmup': max(args.warmup, 3), 'ms_per_step': ms_per_step, 'higher_is_better': True,
@@ -379,11 +410,14 @@ def main():
             'e2e': e2e, 'gpu_launches': args.steps, 'clocks': clocks,
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
                          'traffic': traffic, 'peak_source': peak_src,
-                         'kernel': {'tc': 'k4_march_tc_kernel', 'ws': 'k4_march_ws_kernel'}.get(mode, 'k4_march_kernel'),
+                         'kernel': kernel_name,
                          'kernel_ms_per_launch': kernel_ms,
                          'algorithmic_bytes_per_ray': alg_bytes / (H * W),
                          'samples_per_ray': {'S_m': S_m / (H * W), 'S_d': S_d / (H * W), 'S_c': S_c / (H * W)},
                          'note': 'logical bytes (no reuse credit): the 213 MB scene is L2/L1 resident, so DRAM traffic is far below this'},
+            'roofline_tensor': {'bound': 'tensor', 'achieved': mlp_tflops, 'peak': tp_peak, 'unit': 'TFLOP/s', 'frac': mlp_tflops / tp_peak,
+                                'peak_source': tp_src, 'flops': 'useful rgbnet MACs only: 2 x 21,760 x S_c (padding K 39->48, N 3->16 and bias MMAs not counted)',
+                                'ncu_pct_of_peak': ncu_pct},
         }
         if extra:
             line['extra'] = extra
@@ -432,6 +466,13 @@ def secondary(model, st, model_from_state, kw, dev, mode, args):
                                  'samples_per_ray': {'S_m': c[0] / n, 'S_d': c[1] / n, 'S_c': c[2] / n}}
     del m2, st2, rays4k, dbg
     torch.cuda.empty_cache()
+    # BASELINE.md section 4 "second baseline": the reference's OWN CUDA kernels (oracle/_ref/render_utils_cuda.so, compiled
+    # from /root/reference) + ATen fp32 in the reference's forward structure and 8192-ray chunks (run_sr.py:121-124) on this
+    # same B200 -- the only like-for-like "vs reference" figure (the reference has no CPU path).  Bounded sample.
+    try:
+        out['reference_kernels_gpu'] = reference_kernels_gpu(st, dev, args.regime, out_headline_mode=mode)
+    except Exception as e:
+        out['reference_kernels_gpu'] = {'unavailable': repr(e)}
     # configs[2]: LLFF MPI model [384,384,256], k0 9 ch, rgbnet 15-64-64-3, 256 samples/ray, NDC rays
     try:
         st3 = make_state('cfgB', xy=384, depth=256, regime='shell')
@@ -483,6 +524,36 @@ def secondary(model, st, model_from_state, kw, dev, mode, args):
     return out
 
 
+def reference_kernels_gpu(st, dev, regime, out_headline_mode, n_chunks=32, chunk=8192):
+    from oracle import ops as oops, pipeline, scenes
+    if not os.path.exists(oops.ref_ext_path()):
+        return {'unavailable': 'oracle/_ref/render_utils_cuda.so not built (needs /root/reference at build time)'}
+    ref_ops = oops.RefExtOps()
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False                 # fp32 Linear, as the parity tests
+    st_dev = pipeline.state_to(st, dev)
+    chunks = [tuple(t.to(dev) for t in c) for c in cpu_sample_rays(H4K, W4K, POSES[0], n_chunks, chunk)]
+    kw = dict(scenes.RENDER_KW_DVGO)
+    for c in chunks[:3]:
+        pipeline.forward(st_dev, *c, ref_ops, **kw)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    for c in chunks:
+        pipeline.forward(st_dev, *c, ref_ops, **kw)
+    e1.record()
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    torch.backends.cuda.matmul.allow_tf32 = old
+    ms = e0.elapsed_time(e1)
+    n = n_chunks * chunk
+    return {'rays_per_s': n / (ms * 1e-3), 'ms_per_8192_ray_chunk': ms / n_chunks, 'wall_s': wall,
+            'sample': f'{n_chunks} x {chunk}-ray chunks spread over the 4032x3024 {regime} frame',
+            'what': 'oracle/pipeline.py (the reference forward structure: flat lists, 3 compactions, grid_sample, Linear, index_add) '
+                    'on the reference kernels compiled from /root/reference + ATen fp32, device timed incl. its host syncs'}
+
+
 def secondary_sharded(model, kw, dev, world):
     """configs[4] (N>1): the whole 4K-NeRF frame across the ranks -- 1008x756 marcher (8-row blocks,
     one all-gather) + VC-Decoder x4 sharded by reference tile / tile row-parts (one all-gather).
@@ -522,7 +593,7 @@ def secondary_sharded(model, kw, dev, world):
 def cpu_baseline(st):
     """The oracle port timed on the host cores, bounded sample (rank 0, N=1 only)."""
     from oracle import ops
-    cores = os.cpu_count() or 1
+    cores = cpu_threads()
     ops.set_num_threads(cores)
     chunks = cpu_sample_rays(H4K, W4K, POSES[0], 2)
     cpu_time_step(st, chunks[:1])                 # warm-up

@@ -164,6 +164,13 @@ K4_API int k4_make_rays(const float* h_K, const float* h_c2w, int32_t H, int32_t
                  int32_t inverse_y, int32_t flip_x, int32_t flip_y,
                  float* d_rays_o, float* d_rays_d, float* d_viewdirs, k4_stream_t stream);
 
+/* Same for a subset of the image rows (multi-GPU: a rank generates only ITS rows of the frame, SURVEY.md
+ * section 8e): d_rows = DEVICE array of n_rows image-row indices (NULL = all H rows in order);
+ * outputs are [n_rows*W,3] in the order of d_rows.  Values are identical to the same pixels of k4_make_rays. */
+K4_API int k4_make_rays_rows(const float* h_K, const float* h_c2w, int32_t H, int32_t W, int32_t ndc,
+                 int32_t inverse_y, int32_t flip_x, int32_t flip_y, const int32_t* d_rows, int32_t n_rows,
+                 float* d_rays_o, float* d_rays_d, float* d_viewdirs, k4_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
  * VC-Decoder: SFTNet (lib/sr_esrnet.py:400-465), the x4 SFT-RRDB upsampler that turns the marcher's
  * rgb_feature + depth images into the 4K frame (run_sr.py:1353-1387).

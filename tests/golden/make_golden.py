@@ -57,6 +57,34 @@ def make_sftnet_golden():
     print('sftnet_ref.pt', tuple(y.shape), tuple(yt.shape))
 
 
+def sftnet_pretrained_inputs():
+    g = torch.Generator().manual_seed(12)
+    x = torch.rand(1, 3, 40, 48, generator=g) * 1.2 - 0.1
+    c = torch.rand(1, 1, 40, 48, generator=g)
+    return x, c
+
+
+def make_sftnet_pretrained_golden():
+    """The REFERENCE module with the shipped pretrained/RealESRNet_x4plus.pth loaded exactly as
+    run_sr.py:663 does (load_network(strict=False) on top of the constructor's parameters; here the
+    non-pretrained SFT / CondNet parameters are the seeded set so that a consumer can rebuild them)."""
+    sys.path.insert(0, '/root/reference')
+    from lib import sr_esrnet
+    import io, contextlib
+    net = sr_esrnet.SFTNet(n_in_colors=3, scale=4, num_feat=64, num_block=5, num_grow_ch=32, num_cond=1, dswise=False)
+    net.load_state_dict(sftnet.random_state_dict(seed=3), strict=True)
+    with contextlib.redirect_stdout(io.StringIO()):
+        net.load_network(load_path='/root/reference/pretrained/RealESRNet_x4plus.pth', device='cpu', strict=False)
+    net.eval()
+    x, c = sftnet_pretrained_inputs()
+    with torch.no_grad():
+        y = net(x, c)
+    torch.save({'forward': y.clone(), 'param_seed': 3, 'input_seed': 12,
+                'source': 'reference lib/sr_esrnet.py SFTNet + pretrained/RealESRNet_x4plus.pth (strict=False), torch %s CPU' % torch.__version__},
+               os.path.join(HERE, 'sftnet_pretrained_ref.pt'))
+    print('sftnet_pretrained_ref.pt', tuple(y.shape), float(y.min()), float(y.max()))
+
+
 MARCHER_CASES = {
     'cfgA_fog': ('cfgA', dict(res=24, regime='fog'), (16, 20)),
     'cfgA_shell': ('cfgA', dict(res=24, regime='shell'), (16, 20)),
@@ -86,4 +114,5 @@ def make_marcher_golden():
 
 if __name__ == '__main__':
     make_sftnet_golden()
+    make_sftnet_pretrained_golden()
     make_marcher_golden()

@@ -1,12 +1,19 @@
 """Test helpers: turn an oracle scene state (oracle/pipeline.py dict) into a product model."""
+import os
+
 import torch
 
-import k4nerf
 from oracle import pipeline, scenes
+
+PRETRAINED_SR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'oracle', '_ref',
+                             'RealESRNet_x4plus.pth')
 
 
 def model_from_state(st, device=None):
-    """Build the k4nerf module with the reference constructor kwargs and load the oracle's tensors."""
+    """Build the k4nerf module with the reference constructor kwargs and load the oracle's tensors.
+    (k4nerf is imported here, not at module level: bench.py's reference arm uses the scene helpers of
+    this file and must not map libk4nerf.so.)"""
+    import k4nerf
     if st['kind'] == 'dvgo':
         nvox = int(st['density'].shape[2] * st['density'].shape[3] * st['density'].shape[4])
         kw = dict(xyz_min=st['xyz_min'].tolist(), xyz_max=st['xyz_max'].tolist(),
@@ -95,3 +102,40 @@ def compare(ours, ref, n_rays):
             out[k + '_maxabs'] = (a - b).abs().max().item() if a.numel() else 0.0
             out[k + '_psnr'] = pipeline.psnr(a, b) if a.numel() else float('inf')
     return out
+
+
+def pretrained_sr_state_dict(seed=3):
+    """SFTNet parameters as run_sr.py:663 builds them: a freshly constructed net (here the seeded
+    random_state_dict, so every consumer rebuilds the same set) with pretrained/RealESRNet_x4plus.pth
+    loaded on top, strict=False (the RRDB convs / conv_first / conv_body / up / hr / last come from the
+    checkpoint, the SFT layers and CondNet keep their initial values).  Needs oracle/_ref/RealESRNet_x4plus.pth
+    (copied by oracle/build_ref.py where /root/reference exists); returns None when it is absent."""
+    from oracle import sftnet
+    if not os.path.exists(PRETRAINED_SR):
+        return None
+    sd = sftnet.random_state_dict(seed=seed)
+    ck = torch.load(PRETRAINED_SR, map_location='cpu', weights_only=False)
+    ck = ck['params_ema'] if 'params_ema' in ck else ck['params']
+    n = 0
+    for k, v in ck.items():
+        k = k[7:] if k.startswith('module.') else k
+        if k in sd and sd[k].shape == v.shape:
+            sd[k] = v.float().clone()
+            n += 1
+    assert n >= 160, n
+    return sd
+
+
+def ref_forward_chunked(st_dev, ro, rd, vd, kw, ref_ops, chunk=8192):
+    """The reference's render_viewpoints chunk loop (run_sr.py:121-124: 8192-ray chunks, concatenated)
+    over oracle.pipeline.forward on an op backend; returns the concatenated per-ray outputs, the per-ray
+    visited-sample counts and the summed sample statistics."""
+    outs = {'rgb_marched': [], 'alphainv_last': [], 'depth': [], '_ray_stats': []}
+    stats = {}
+    for s in range(0, ro.shape[0], chunk):
+        r = pipeline.forward(st_dev, ro[s:s + chunk].contiguous(), rd[s:s + chunk].contiguous(),
+                             vd[s:s + chunk].contiguous(), ref_ops, stats=stats, **kw)
+        for k in outs:
+            if k in r:
+                outs[k].append(r[k].clone())
+    return {k: torch.cat(v) for k, v in outs.items() if v}, stats

@@ -39,6 +39,18 @@ def _worker(rank, world, port, H, W, q):
     for layout in ('cyclic', 'bands'):
         full = kdist.render_frame_sharded(_fake_render, ro, rd, vd, H, W, layout=layout)
         ok = ok and all(torch.equal(full[k], ref[k]) for k in ('rgb_marched', 'depth', 'alphainv_last'))
+    # the device-resident driver's path: only the rank's rows are "generated", the render writes into the
+    # packed buffer's views, one all-gather, image-order transpose
+    frame = kdist.CyclicFrame(H, W, torch.device('cpu'))
+    make = lambda rows: tuple(t.view(H, W, 3)[rows.long()].reshape(-1, 3) for t in (ro, rd, vd))
+
+    def render_into(a, b, c, hw, out):
+        r = _fake_render(a, b, c, hw)
+        for k in out:
+            out[k].copy_(r[k])
+    for _ in range(2):                                   # buffers are reused across frames
+        full = frame.render(make, render_into)
+        ok = ok and all(torch.equal(full[k], ref[k]) for k in ('rgb_marched', 'depth', 'alphainv_last'))
     r0, r1 = kdist.band_range(H, rank, world)
     q.put((rank, ok, r0, r1))
     dist.destroy_process_group()

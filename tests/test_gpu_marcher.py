@@ -183,21 +183,5 @@ def test_make_rays_matches_reference_formulas(cuda_device):
                 assert (a.cpu() - b).abs().max().item() <= 2e-6 * max(1.0, b.abs().max().item())
 
 
-@pytest.mark.parametrize('regime', ['fog', 'shell'])
-@pytest.mark.parametrize('mode', ['tc', 'ws'])
-def test_persistent_multi_tile_matches_generic_kernel(cuda_device, regime, mode):
-    """More 128-ray tiles than warpgroups on the chip (both warpgroups of every CTA busy, several
-    tiles each, ragged batches): the tcgen05 kernels against the generic mma.sync kernel."""
-    dev = cuda_device
-    st = make_state('cfgA', res=48, regime=regime)
-    (ro, rd, vd), kw = rays_for(st, 300, 400)
-    m = model_from_state(st, dev)
-    ro, rd, vd = ro.to(dev), rd.to(dev), vd.to(dev)
-    for hw in ((300, 400), None):
-        a = m.render_rays(ro, rd, vd, kw, image_hw=hw, mlp_mode='f16', debug=True)
-        b = m.render_rays(ro, rd, vd, kw, image_hw=hw, mlp_mode=mode, debug=True)
-        torch.cuda.synchronize()
-        assert torch.equal(a['counters'][:3], b['counters'][:3])
-        assert torch.equal(a['ray_stats'], b['ray_stats'])
-        assert torch.equal(a['alphainv_last'], b['alphainv_last']) and torch.equal(a['depth'], b['depth'])
-        assert (a['rgb_marched'] - b['rgb_marched']).abs().max().item() < 3e-5
+# (the persistent multi-tile case lives in test_gpu_scale.py::test_persistent_multi_tile_vs_gpu_oracle, against the
+# reference kernels' pipeline instead of the repo's own mma.sync kernel)

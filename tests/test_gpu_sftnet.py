@@ -9,6 +9,7 @@ import torch
 
 import k4nerf
 from oracle import pipeline, sftnet
+from helpers import pretrained_sr_state_dict
 
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
@@ -101,3 +102,97 @@ def test_row_parts_with_halo_reproduce_the_unsplit_tile(net, cuda_device, world)
     # and through the collective-free single-process path of the sharded driver
     full = net.tile_process_sharded(x, c, tile_size=510, tile_pad=10)
     assert torch.equal(full, ref)
+
+
+# ------------------------------------------------------------------------------------------------
+# real weights, real sizes (VERDICT r1 "weak" #1): pretrained/RealESRNet_x4plus.pth loaded strict=False as
+# run_sr.py:663 does, the reference's largest tile (520x520) and the whole 1008x756 tile_process(510),
+# against oracle.sftnet on cuDNN in true fp32 (TF32 off).  Bar: >= 65 dB; the reference's own default
+# arithmetic (cuDNN TF32) is measured beside it on the same input for context.
+# ------------------------------------------------------------------------------------------------
+@pytest.fixture(scope='module')
+def net_pretrained(cuda_device):
+    sd = pretrained_sr_state_dict()
+    if sd is None:
+        pytest.skip('oracle/_ref/RealESRNet_x4plus.pth missing (python oracle/build_ref.py where /root/reference exists)')
+    n = k4nerf.SFTNet(3, 4, 64, 5, 32, 1)
+    n.load_state_dict(sd)
+    return n.to(cuda_device), {k: v.to(cuda_device) for k, v in sd.items()}
+
+
+def _fp32_and_tf32(fn):
+    """fn() evaluated with cuDNN/cuBLAS in true fp32 and in the reference's default TF32 mode."""
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    try:
+        torch.backends.cudnn.allow_tf32 = False; torch.backends.cuda.matmul.allow_tf32 = False
+        a = fn()
+        torch.backends.cudnn.allow_tf32 = True; torch.backends.cuda.matmul.allow_tf32 = True
+        b = fn()
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+    return a, b
+
+
+def test_pretrained_forward_matches_reference_module_golden(net_pretrained, cuda_device):
+    """Golden vector produced by the REFERENCE module with the shipped checkpoint (tests/golden/make_golden.py)."""
+    net, _ = net_pretrained
+    gold = torch.load(os.path.join(GOLD, 'sftnet_pretrained_ref.pt'), map_location='cpu', weights_only=False)
+    g = torch.Generator().manual_seed(12)
+    x = torch.rand(1, 3, 40, 48, generator=g) * 1.2 - 0.1
+    c = torch.rand(1, 1, 40, 48, generator=g)
+    y = net(x.to(cuda_device), c.to(cuda_device)).cpu()
+    p = pipeline.psnr(y, gold['forward'])
+    print('pretrained SFTNet vs reference-module golden: PSNR', p, 'maxabs', (y - gold['forward']).abs().max().item())
+    assert p >= 65.0, p
+
+
+def test_pretrained_520_tile_vs_cudnn_fp32(net_pretrained, cuda_device):
+    net, sd = net_pretrained
+    g = torch.Generator().manual_seed(31)
+    x = (torch.rand(1, 3, 520, 520, generator=g) * 1.2 - 0.1).to(cuda_device)
+    c = torch.rand(1, 1, 520, 520, generator=g).to(cuda_device)
+    ref32, ref_tf32 = _fp32_and_tf32(lambda: sftnet.sftnet_forward(sd, x, c))
+    y = net(x, c)
+    p, p_tf32 = pipeline.psnr(y.cpu(), ref32.cpu()), pipeline.psnr(ref_tf32.cpu(), ref32.cpu())
+    print(f'520x520 tile, pretrained weights: k4nerf vs cuDNN fp32 {p:.2f} dB (maxabs {(y - ref32).abs().max().item():.3e}); '
+          f'cuDNN TF32 (the reference default) vs cuDNN fp32 {p_tf32:.2f} dB')
+    assert y.shape == (1, 3, 2080, 2080)
+    assert p >= 65.0, (p, p_tf32)
+
+
+def test_pretrained_full_frame_tile_process_vs_cudnn_fp32(net_pretrained, cuda_device):
+    """BASELINE.json configs[3]: 1008x756 -> 4032x3024, tile 510 / pad 10 (run_sr.py --test_tile 510)."""
+    net, sd = net_pretrained
+    g = torch.Generator().manual_seed(32)
+    x = (torch.rand(1, 3, 756, 1008, generator=g) * 1.2 - 0.1).to(cuda_device)
+    c = torch.rand(1, 756, 1008, generator=g).to(cuda_device)
+    ref32, ref_tf32 = _fp32_and_tf32(lambda: sftnet.tile_process(sd, x, c, 510, 10))
+    y = net.tile_process(x, c, 510, 10)
+    assert y.shape == (1, 3, 3024, 4032) and y.device.type == 'cpu'
+    p, p_tf32 = pipeline.psnr(y, ref32), pipeline.psnr(ref_tf32, ref32)
+    print(f'1008x756 tile_process(510), pretrained weights: k4nerf vs cuDNN fp32 {p:.2f} dB; cuDNN TF32 vs fp32 {p_tf32:.2f} dB')
+    assert p >= 65.0, (p, p_tf32)
+
+
+def test_large_magnitude_activations_do_not_overflow_fp16(cuda_device):
+    """Conv / SFT operands are fp16: weights scaled so that the trunk reaches ~1e3 and the SFT modulation
+    multiplies it further.  Every fp32 -> fp16 conversion in the kernels saturates (cvt.rn.satfinite), so no
+    inf/nan may appear and the result must stay close to the fp32 network wherever the fp32 network's own
+    intermediate values are representable."""
+    sd = sftnet.random_state_dict(seed=5, scale=1.0)
+    for k in sd:
+        if k.startswith('conv_first'):
+            sd[k] = sd[k] * 400.0
+    n = k4nerf.SFTNet(3, 4, 64, 5, 32, 1)
+    n.load_state_dict(sd)
+    n = n.to(cuda_device)
+    g = torch.Generator().manual_seed(6)
+    x = torch.rand(1, 3, 40, 56, generator=g).to(cuda_device)
+    c = torch.rand(1, 1, 40, 56, generator=g).to(cuda_device)
+    sdd = {k: v.to(cuda_device) for k, v in sd.items()}
+    ref32, _ = _fp32_and_tf32(lambda: sftnet.sftnet_forward(sdd, x, c))
+    y = n(x, c)
+    assert torch.isfinite(y).all(), 'fp16 overflow in the decoder'
+    rel = (y - ref32).abs().max().item() / ref32.abs().max().item()
+    print('large-magnitude decoder: ref range', ref32.abs().max().item(), 'rel maxabs', rel)
+    assert rel <= 2e-2, rel

@@ -37,6 +37,24 @@ def test_sftnet_oracle_matches_reference_module_output():
     assert (yt - gold['tile_process']).abs().max().item() <= 2e-5
 
 
+def test_sftnet_oracle_with_pretrained_weights_matches_reference_module():
+    """sftnet_pretrained_ref.pt: the REFERENCE module with pretrained/RealESRNet_x4plus.pth loaded
+    strict=False as run_sr.py:663 does.  The checkpoint travels as oracle/_ref/RealESRNet_x4plus.pth
+    (git-ignored, copied by oracle/build_ref.py); skipped where it is absent."""
+    import pytest
+    from helpers import pretrained_sr_state_dict
+    sd = pretrained_sr_state_dict()
+    if sd is None:
+        pytest.skip('oracle/_ref/RealESRNet_x4plus.pth missing')
+    gold = _load('sftnet_pretrained_ref.pt')
+    g = torch.Generator().manual_seed(gold['input_seed'])
+    x = torch.rand(1, 3, 40, 48, generator=g) * 1.2 - 0.1
+    c = torch.rand(1, 1, 40, 48, generator=g)
+    y = sftnet.sftnet_forward(sd, x, c)
+    assert y.shape == gold['forward'].shape
+    assert (y - gold['forward']).abs().max().item() <= 2e-5
+
+
 def test_tile_plan_geometry():
     # 1008x756 with tile 510 / pad 10 -> 2x2 tiles (SURVEY.md section 3.1)
     plan = sftnet.tile_plan(756, 1008, 510, 10)
