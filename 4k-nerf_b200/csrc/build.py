@@ -12,7 +12,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 OUT = os.path.join(os.path.dirname(HERE), 'k4nerf', 'libk4nerf.so')
 SOURCES = ['k4_capi.cu', 'k4_march.cu', 'k4_march_tc.cu', 'k4_march_ws.cu', 'k4_sr.cu', 'k4_ops.cu', 'k4_train.cu']
-HEADERS = ['k4_internal.cuh', 'k4_march_common.cuh', 'k4_march_mma.cuh', '../../include/k4nerf.h']
+HEADERS = ['k4_internal.cuh', 'k4_march_common.cuh', 'k4_march_mma.cuh', 'k4_ws_cfgs.h', '../../include/k4nerf.h']
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
 FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
          '-Xcompiler', '-fPIC,-fvisibility=hidden', '--expt-relaxed-constexpr', '-Xptxas', '-v',

@@ -8,6 +8,7 @@
 
 #include "k4_internal.cuh"
 #include "k4_march_mma.cuh"
+#include "k4_ws_cfgs.h"
 
 // ------------------------------------------------------------------------------------------------
 // errors
@@ -81,13 +82,45 @@ __global__ void pack_w_f16_kernel(const float* __restrict__ W, __half* __restric
 }
 
 // tcgen05 operand tiles (canonical K-major, no swizzle; see tc_canon_off)
+// The destination tile is pre-zeroed; model weight (n, k) lands at column colmap[k] (identity when colmap == nullptr):
+// the config's row layout may hold more inputs than the model has (k4_ws_cfgs.h), those columns stay zero.
 __global__ void pack_tc_weight_kernel(const float* __restrict__ W, unsigned char* __restrict__ dst,
-                                      int n_out, int n_in, int npad, int kpad) {
+                                      int n_out, int n_in, int kpad, const int* __restrict__ colmap) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= npad * kpad) return;
-    const int n = i / kpad, k = i - n * kpad;
-    const float w = (n < n_out && k < n_in) ? W[(size_t)n * n_in + k] : 0.f;
-    *reinterpret_cast<__half*>(dst + tc_canon_off(n, k >> 3, kpad >> 3) + (k & 7) * 2) = __float2half_rn(w);
+    if (i >= n_out * n_in) return;
+    const int n = i / n_in, k = i - n * n_in;
+    const int kd = colmap ? colmap[k] : k;
+    *reinterpret_cast<__half*>(dst + tc_canon_off(n, kd >> 3, kpad >> 3) + (kd & 7) * 2) = __float2half_rn(W[i]);
+}
+
+// ---- empty-space skipping: coarse occupancy of the mask and its Chebyshev distance field ----
+__global__ void skip_coarse_kernel(const uint8_t* __restrict__ mask, uint8_t* __restrict__ dist, int mX, int mY, int mZ,
+                                   int cX, int cY, int cZ) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= cX * cY * cZ) return;
+    const int cz = c % cZ, cy = (c / cZ) % cY, cx = c / (cZ * cY);
+    bool any = false;
+    for (int i = cx * K4_SKIP_B; i < min((cx + 1) * K4_SKIP_B, mX) && !any; ++i)
+        for (int j = cy * K4_SKIP_B; j < min((cy + 1) * K4_SKIP_B, mY) && !any; ++j)
+            for (int k = cz * K4_SKIP_B; k < min((cz + 1) * K4_SKIP_B, mZ); ++k)
+                if (mask[((size_t)i * mY + j) * mZ + k]) { any = true; break; }
+    dist[c] = any ? 0 : 255;
+}
+// pass p: an unset cell with a neighbour (3x3x3) of distance <= p-1 gets distance p.  In place: values written in
+// this pass are p, never <= p-1, so the order of the threads does not matter.
+__global__ void skip_dilate_kernel(uint8_t* __restrict__ dist, int cX, int cY, int cZ, int p) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= cX * cY * cZ) return;
+    if (dist[c] != 255) return;
+    const int cz = c % cZ, cy = (c / cZ) % cY, cx = c / (cZ * cY);
+    for (int i = max(cx - 1, 0); i <= min(cx + 1, cX - 1); ++i)
+        for (int j = max(cy - 1, 0); j <= min(cy + 1, cY - 1); ++j)
+            for (int k = max(cz - 1, 0); k <= min(cz + 1, cZ - 1); ++k)
+                if (dist[((size_t)i * cY + j) * cZ + k] <= p - 1) { dist[c] = (uint8_t)p; return; }
+}
+__global__ void skip_cap_kernel(uint8_t* __restrict__ dist, int n) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < n && dist[c] == 255) dist[c] = K4_SKIP_MAXD + 1;
 }
 // bias tile [npad][16]: col 0 = fp16(b), col 1 = fp16(b - col0); multiplied by the ONES tile (cols 0,1 = 1)
 __global__ void pack_tc_bias_kernel(const float* __restrict__ b, unsigned char* __restrict__ dst, int n_out, int npad) {
@@ -195,6 +228,17 @@ extern "C" int k4_scene_destroy(k4_scene* sc) {
 
 extern "C" size_t k4_scene_device_bytes(const k4_scene* sc) { return sc ? sc->bytes : 0; }
 
+extern "C" int k4_scene_best_mlp_mode(const k4_scene* sc) {
+    if (!sc) return K4_ERR_INVALID_ARG;
+    const K4Dev& v = sc->dev;
+    if (v.depth == 0) return K4_MLP_FP32;
+    if (k4_ws_supported(v)) return K4_MLP_TCGEN05_WS;
+    if (MmaWarpCtx<K4_MLP_F16>::supported(v)) return K4_MLP_F16;
+    return K4_MLP_FP32;
+}
+
+extern "C" int k4_scene_ws_config(const k4_scene* sc) { return sc ? sc->dev.tc_cfg : -1; }
+
 extern "C" int k4_scene_create(const k4_scene_desc* d, k4_stream_t stream, k4_scene** out) {
     if (!d || !out) return K4_ERR_INVALID_ARG;
     *out = nullptr;
@@ -220,6 +264,13 @@ extern "C" int k4_scene_create(const k4_scene_desc* d, k4_stream_t stream, k4_sc
     v.kind = d->kind;
     v.X = d->world_size[0]; v.Y = d->world_size[1]; v.Z = d->world_size[2];
     v.C = d->k0_dim; v.Cpad = round_up(d->k0_dim, 4);
+    // tcgen05 config this model runs on (k4_ws_cfgs.h): its k0 copy is padded to the config's channel count
+    const K4WsCfg* wcfg = (d->rgbnet_depth > 0)
+        ? k4_ws_pick(d->kind, d->k0_dim, d->viewbase_pe, d->kind == K4_KIND_DMPIGO ? d->spatial_pe : 0, d->rgbnet_width,
+                     d->kind == K4_KIND_DVGO ? (d->rgbnet_direct != 0) : 1, d->rgbnet_depth)
+        : nullptr;
+    if (wcfg && round_up(wcfg->C, 4) > v.Cpad) v.Cpad = round_up(wcfg->C, 4);
+    v.tc_cfg = -1; v.tc_exact = 0;
     v.mX = d->mask_size[0]; v.mY = d->mask_size[1]; v.mZ = d->mask_size[2];
     for (int a = 0; a < 3; ++a) {
         v.xyz_min[a] = d->xyz_min[a]; v.xyz_max[a] = d->xyz_max[a];
@@ -255,6 +306,29 @@ extern "C" int k4_scene_create(const k4_scene_desc* d, k4_stream_t stream, k4_sc
         K4_CTRY(cudaMemcpyAsync(p_act, d->d_act_shift_grid, (size_t)d->mpi_depth * 4, cudaMemcpyDeviceToDevice, s));
     }
     v.density = p_density; v.k0cl = p_k0; v.mask = p_mask; v.act_grid = p_act;
+
+    // ---- empty-space skipping: distance field over K4_SKIP_B^3-voxel cells of the occupancy mask ----
+    v.skip = nullptr; v.cX = v.cY = v.cZ = 0;
+    {
+        bool ok = d->kind != K4_KIND_DCVGO && getenv("K4_NO_SKIP") == nullptr;   // contracted sampling carries per-step state
+        for (int a = 0; a < 3; ++a) {
+            ok = ok && v.m_scale[a] > 0.f;
+            v.m_iscale[a] = v.m_scale[a] > 0.f ? 1.f / v.m_scale[a] : 0.f;
+        }
+        if (ok) {
+            v.cX = (v.mX + K4_SKIP_B - 1) / K4_SKIP_B; v.cY = (v.mY + K4_SKIP_B - 1) / K4_SKIP_B; v.cZ = (v.mZ + K4_SKIP_B - 1) / K4_SKIP_B;
+            const int nc = v.cX * v.cY * v.cZ;
+            uint8_t* p_skip = nullptr;
+            K4_TRY(scene_alloc(sc, (void**)&p_skip, (size_t)nc));
+            skip_coarse_kernel<<<(nc + 127) / 128, 128, 0, s>>>(p_mask, p_skip, v.mX, v.mY, v.mZ, v.cX, v.cY, v.cZ);
+            int maxc = v.cX > v.cY ? v.cX : v.cY; if (v.cZ > maxc) maxc = v.cZ;
+            const int passes = maxc < K4_SKIP_MAXD ? maxc : K4_SKIP_MAXD;
+            for (int p = 1; p <= passes; ++p) skip_dilate_kernel<<<(nc + 127) / 128, 128, 0, s>>>(p_skip, v.cX, v.cY, v.cZ, p);
+            skip_cap_kernel<<<(nc + 127) / 128, 128, 0, s>>>(p_skip, nc);
+            K4_CTRY(cudaGetLastError());
+            v.skip = p_skip;
+        }
+    }
 
     // ---- rgbnet ----
     v.dim0 = 0; v.k0_view_off = 0;
@@ -306,22 +380,43 @@ extern "C" int k4_scene_create(const k4_scene_desc* d, k4_stream_t stream, k4_sc
                     v.wh[l] = ph; v.wl[l] = pl;
                 }
             }
-            // tcgen05 blob (k4_march_tc.cu): only for the shapes that kernel is instantiated for
-            if ((v.width == 128 || v.width == 64) && dim0 <= 64) {
-                const int kpad = round_up(dim0, 16), w = v.width;
+            // tcgen05 operand blob, packed for the K4_WS_CFG_LIST entry that covers this model (k4_ws_cfgs.h)
+            if (wcfg) {
+                const K4WsCfg& c = *wcfg;
+                const int kpad = k4_ws_kpad(c), w = c.W, nsp = k4_ws_nsp(c);
+                // model input column -> row column of the config's layout
+                int colmap[K4_MAX_DIM0];
+                const int k0_in = v.C - v.k0_view_off;
+                int k = 0;
+                for (int j = 0; j < k0_in; ++j) colmap[k++] = j;
+                if (d->kind == K4_KIND_DMPIGO) {          // [k0, p(3), sin(p f), cos(p f), view emb]  (lib/dmpigo.py:347-351,374)
+                    const int pb = c.C;
+                    for (int a = 0; a < 3; ++a) colmap[k++] = pb + a;
+                    for (int a = 0; a < 3; ++a) for (int q = 0; q < v.spape; ++q) colmap[k++] = pb + 3 + a * c.spe + q;
+                    for (int a = 0; a < 3; ++a) for (int q = 0; q < v.spape; ++q) colmap[k++] = pb + 3 + 3 * c.spe + a * c.spe + q;
+                }
+                for (int a = 0; a < 3; ++a) colmap[k++] = nsp + a;                              // viewdirs
+                for (int a = 0; a < 3; ++a) for (int f = 0; f < v.viewpe; ++f) colmap[k++] = nsp + 3 + a * c.vpe + f;
+                for (int a = 0; a < 3; ++a) for (int f = 0; f < v.viewpe; ++f) colmap[k++] = nsp + 3 + 3 * c.vpe + a * c.vpe + f;
+                if (k != dim0) { k4_scene_destroy(sc); return K4_ERR_INVALID_ARG; }
+                int* d_colmap = nullptr;
+                K4_TRY(scene_alloc(sc, (void**)&d_colmap, sizeof(int) * K4_MAX_DIM0));
+                K4_CTRY(cudaMemcpyAsync(d_colmap, colmap, sizeof(int) * dim0, cudaMemcpyHostToDevice, s));
                 const TcBlobLayout BL = tc_blob_layout(kpad, w);
                 unsigned char* blob = nullptr;
                 K4_TRY(scene_alloc(sc, (void**)&blob, (size_t)BL.total));
                 K4_CTRY(cudaMemsetAsync(blob, 0, BL.total, s));
-                pack_tc_weight_kernel<<<(w * kpad + 255) / 256, 256, 0, s>>>(d->d_rgbnet_weight[0], blob + BL.off_w1, w, dim0, w, kpad);
-                pack_tc_weight_kernel<<<(w * w + 255) / 256, 256, 0, s>>>(d->d_rgbnet_weight[1], blob + BL.off_w2, w, w, w, w);
-                pack_tc_weight_kernel<<<(16 * w + 255) / 256, 256, 0, s>>>(d->d_rgbnet_weight[2], blob + BL.off_w3, 3, w, 16, w);
-                pack_tc_bias_kernel<<<(w * 16 + 255) / 256, 256, 0, s>>>(d->d_rgbnet_bias[0], blob + BL.off_b1, w, w);
-                pack_tc_bias_kernel<<<(w * 16 + 255) / 256, 256, 0, s>>>(d->d_rgbnet_bias[1], blob + BL.off_b2, w, w);
+                const int wm = v.width;
+                pack_tc_weight_kernel<<<(wm * dim0 + 255) / 256, 256, 0, s>>>(d->d_rgbnet_weight[0], blob + BL.off_w1, wm, dim0, kpad, d_colmap);
+                pack_tc_weight_kernel<<<(wm * wm + 255) / 256, 256, 0, s>>>(d->d_rgbnet_weight[1], blob + BL.off_w2, wm, wm, w, nullptr);
+                pack_tc_weight_kernel<<<(3 * wm + 255) / 256, 256, 0, s>>>(d->d_rgbnet_weight[2], blob + BL.off_w3, 3, wm, w, nullptr);
+                pack_tc_bias_kernel<<<(w * 16 + 255) / 256, 256, 0, s>>>(d->d_rgbnet_bias[0], blob + BL.off_b1, wm, w);
+                pack_tc_bias_kernel<<<(w * 16 + 255) / 256, 256, 0, s>>>(d->d_rgbnet_bias[1], blob + BL.off_b2, wm, w);
                 pack_tc_bias_kernel<<<1, 256, 0, s>>>(d->d_rgbnet_bias[2], blob + BL.off_b3, 3, 16);
                 pack_tc_ones_kernel<<<8, 256, 0, s>>>(blob + BL.off_ones);
                 K4_CTRY(cudaGetLastError());
-                v.tc_blob = blob; v.tc_kpad = kpad; v.tc_width = w;
+                v.tc_blob = blob; v.tc_kpad = kpad; v.tc_width = w; v.tc_cfg = c.id;
+                v.tc_exact = (c.C == v.C && c.vpe == v.viewpe && c.spe == v.spape && c.W == v.width) ? 1 : 0;
             }
         }
     }

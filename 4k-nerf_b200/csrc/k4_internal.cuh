@@ -5,6 +5,8 @@
 #include <stdint.h>
 #include "../../include/k4nerf.h"
 
+#define K4_SKIP_B 4               // occupancy voxels per skip cell edge
+#define K4_SKIP_MAXD 48           // distance-field cap (cells); larger true distances are stored as the cap
 #define K4_MAX_WIDTH 256          // widest hidden layer the fp32 path accepts
 #define K4_MAX_DIM0 128           // widest MLP input the fp32 path accepts
 
@@ -35,6 +37,13 @@ struct K4Dev {
     // tcgen05 pack: one blob of canonical K-major (no swizzle) UMMA operand tiles, see tc_blob_layout()
     const unsigned char* tc_blob;
     int tc_kpad, tc_width;
+    int tc_cfg;                   // id of the K4_WS_CFG_LIST entry (k4_ws_cfgs.h) the blob is packed for, -1: none
+    int tc_exact;                 // the model's own shape equals that entry's (k4_march_tc.cu only runs exact shapes)
+    // empty-space skipping (k4_march_common.cuh skip_steps): Chebyshev distance field over K4_SKIP_B^3-voxel cells of
+    // the occupancy mask, in cells: 0 = the cell holds an occupied voxel, d = every cell within d-1 is empty
+    const uint8_t* skip;          // [cX,cY,cZ] or nullptr (skipping off)
+    int cX, cY, cZ;
+    float m_iscale[3];            // 1 / m_scale
     // DirectContractedVoxGO (lib/dcvgo.py)
     float scene_center[3], scene_radius[3], bg_len, one_plus_bg;
     int world_len;

@@ -195,8 +195,15 @@ k4_march_kernel(const __grid_constant__ K4Dev s, const __grid_constant__ K4Rende
                     const int mj = (int)roundf(__fmaf_rn(py, s.m_scale[1], s.m_shift[1]));
                     const int mk = (int)roundf(__fmaf_rn(pz, s.m_scale[2], s.m_shift[2]));
                     bool occ = false;
-                    if ((0 <= mi) & (mi < s.mX) & (0 <= mj) & (mj < s.mY) & (0 <= mk) & (mk < s.mZ))
-                        occ = __ldg(s.mask + ((size_t)mi * s.mY + mj) * s.mZ + mk) != 0;
+                    const bool in_mask = (0 <= mi) & (mi < s.mX) & (0 <= mj) & (mj < s.mY) & (0 <= mk) & (mk < s.mZ);
+                    if (in_mask) occ = __ldg(s.mask + ((size_t)mi * s.mY + mj) * s.mZ + mk) != 0;
+                    if (KIND != K4_KIND_DCVGO && !occ && in_mask && s.skip) {
+                        // empty-space skipping (k4_march_common.cuh): the next n samples are in-box and unoccupied
+                        const float h = (KIND == K4_KIND_DVGO) ? rp.stepdist : __fdiv_rn(1.f, mpi_den);
+                        const int n = skip_steps(s, mi, mj, mk, r.sx, r.sy, r.sz, r.dx * h, r.dy * h, r.dz * h, i, r.n_steps);
+                        cnt_m += n;
+                        i += n;
+                    }
                     if (occ) {
                         ++cnt_d;
                         cell = make_cell(s, px, py, pz);

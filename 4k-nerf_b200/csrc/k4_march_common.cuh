@@ -127,6 +127,51 @@ __device__ __forceinline__ void interp_k0(const K4Dev& s, const float w[8], cons
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Empty-space skipping (result preserving).  Called for a sample at step i that is inside the bounding box, maps to
+// occupancy voxel (mi, mj, mk) and found it EMPTY.  s.skip holds, per cell of K4_SKIP_B^3 occupancy voxels, the
+// Chebyshev distance d (in cells) to the nearest cell that contains an occupied voxel; d >= 1 means every voxel of the
+// (2d-1)^3 cells around this one is empty.  Sample j of the ray sits at A + D*j (A = ray start, D = direction * step
+// length).  The function returns n such that samples i+1 .. i+n
+//   * lie inside that empty voxel region, whose faces are at half-integer voxel coordinates because the reference looks
+//     up the NEAREST voxel (round(p*scale+shift), render_utils_kernel.cu:385-390), and
+//   * lie inside the scene's bounding box (so each of them counts as an in-box sample, exactly as if it had been visited),
+// both with a safety margin of 1e-3 voxel / 1e-3 step, three orders of magnitude above the rounding error of the sample
+// position.  Such samples fail the occupancy test in the reference pipeline and contribute nothing; the caller adds n
+// to its in-box counter and jumps.  n = 0 is always a correct answer.
+// ---------------------------------------------------------------------------------------------
+// one axis: false = the current sample is not safely inside the region on this axis (no skip at all)
+__device__ __forceinline__ bool skip_axis(int c, int d, int msz, float shift, float iscale, float bmin, float bmax,
+                                          float A, float D, float fi, float& s_exit) {
+    // voxel index range of the empty region on this axis, clipped to the mask; world-space faces at -+0.5 voxel
+    const int lo_v = max((c - d + 1) * K4_SKIP_B, 0), hi_v = min((c + d) * K4_SKIP_B - 1, msz - 1);
+    const float eps = 1e-3f * iscale;
+    const float lo = fmaxf(((float)lo_v - 0.5f - shift) * iscale, bmin) + eps;
+    const float hi = fminf(((float)hi_v + 0.5f - shift) * iscale, bmax) - eps;
+    const float cur = fmaf(D, fi, A);
+    if (!(cur >= lo && cur <= hi)) return false;
+    if (D > 0.f) s_exit = fminf(s_exit, __fdividef(hi - A, D));
+    else if (D < 0.f) s_exit = fminf(s_exit, __fdividef(lo - A, D));
+    return true;
+}
+
+__device__ __forceinline__ int skip_steps(const K4Dev& s, int mi, int mj, int mk, float ax, float ay, float az,
+                                          float dx, float dy, float dz, int i, int n_steps) {
+    const int ci = mi / K4_SKIP_B, cj = mj / K4_SKIP_B, ck = mk / K4_SKIP_B;
+    const int d = __ldg(s.skip + ((size_t)ci * s.cY + cj) * s.cZ + ck);
+    if (d == 0) return 0;
+    const float fi = (float)i;
+    float s_exit = 3.0e38f;
+    if (!skip_axis(ci, d, s.mX, s.m_shift[0], s.m_iscale[0], s.xyz_min[0], s.xyz_max[0], ax, dx, fi, s_exit)) return 0;
+    if (!skip_axis(cj, d, s.mY, s.m_shift[1], s.m_iscale[1], s.xyz_min[1], s.xyz_max[1], ay, dy, fi, s_exit)) return 0;
+    if (!skip_axis(ck, d, s.mZ, s.m_shift[2], s.m_iscale[2], s.xyz_min[2], s.xyz_max[2], az, dz, fi, s_exit)) return 0;
+    // samples with parameter j <= s_exit - 1e-3 are inside; never past the ray's last sample
+    float jm = floorf(s_exit - 1e-3f);
+    jm = fminf(jm, (float)(n_steps - 1));
+    const int n = (int)(jm - fi);
+    return n > 0 ? n : 0;
+}
+
 // torch.norm(dim=-1) of a 3-vector on CUDA: the reduction accumulates acc = fma(x, x, acc) in element
 // order from 0, then sqrt (ATen norm_two ops compiled with fmad).
 __device__ __forceinline__ float l2norm3_aten(float x, float y, float z) {

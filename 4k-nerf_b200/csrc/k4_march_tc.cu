@@ -533,7 +533,7 @@ template <class Cfg>
 bool matches(const K4Dev& v) {
     return v.kind == Cfg::KIND && v.C == Cfg::C && v.viewpe == Cfg::VIEWPE && v.width == Cfg::W && v.depth == 3 &&
            v.dim0 == Cfg::DIM0 && (Cfg::KIND == K4_KIND_DMPIGO ? v.spape == Cfg::SPAPE : v.direct != 0) &&
-           v.tc_blob != nullptr && v.tc_kpad == Cfg::KPAD;
+           v.tc_blob != nullptr && v.tc_kpad == Cfg::KPAD && v.tc_exact != 0;
 }
 
 }  // namespace

@@ -17,6 +17,7 @@
 // Arithmetic is identical to k4_march_tc.cu (same rows, same MMAs, same epilogues).
 #include "k4_internal.cuh"
 #include "k4_march_common.cuh"
+#include "k4_ws_cfgs.h"
 
 namespace {
 
@@ -26,20 +27,25 @@ constexpr int TC_TILES = 3;
 constexpr int TC_RING = TC_TILES * 128;
 constexpr int TC_ROUND = 8;          // marching steps between warpgroup rendezvous when nothing is pending
 
-template <int KIND_, int C_, int VIEWPE_, int SPAPE_, int W_>
+// One entry of K4_WS_CFG_LIST (k4_ws_cfgs.h).  Row layout of the A operand (fp16): [per-sample features: k0 channels
+// K0OFF..C-1, MPI position + its sin/cos, zero-padded to an even count NS][view embedding: v, sin, cos (NVEMB)][zeros to KPAD].
+template <int ID_, int KIND_, int C_, int VIEWPE_, int SPAPE_, int W_, int DIRECT_>
 struct TcCfg {
-    static constexpr int KIND = KIND_, C = C_, VIEWPE = VIEWPE_, SPAPE = SPAPE_, W = W_;
+    static constexpr int ID = ID_, KIND = KIND_, C = C_, VIEWPE = VIEWPE_, SPAPE = SPAPE_, W = W_, DIRECT = DIRECT_;
     static constexpr int CPAD = (C + 3) & ~3;
     static constexpr int NVEMB = 3 + 6 * VIEWPE;
     static constexpr int NPOS = (KIND == K4_KIND_DMPIGO) ? 3 + 6 * SPAPE : 0;
-    static constexpr int NS = C + NPOS;                 // per-sample features (must be even)
+    static constexpr int K0OFF = DIRECT ? 0 : 3;        // rgbnet_direct=False: k0[0:3] is the diffuse logit (lib/dvgo.py:385-386,412)
+    static constexpr int NS0 = C - K0OFF + NPOS;        // per-sample features
+    static constexpr int NS = (NS0 + 1) & ~1;           // ... padded to an even count (rows are packed as fp16 pairs)
+    static constexpr int NF = ((CPAD > C + NPOS) ? CPAD : C + NPOS) + 1;   // feature scratch (k0 quads, position code, pad)
     static constexpr int DIM0 = NS + NVEMB;
     static constexpr int KPAD = (DIM0 + 15) & ~15;
     static constexpr int KCH = KPAD / 8;                // 16-byte chunks per A row
     static constexpr int NVW = (NVEMB + 1) / 2;         // packed per-ray words
     static constexpr int TILE_BYTES = 128 * KPAD * 2;
-    static_assert(NS % 2 == 0, "per-sample feature count must be even for the packed row layout");
     static_assert(W == 128 || W == 64, "hidden width");
+    static_assert(DIRECT || KIND == K4_KIND_DVGO, "the diffuse term exists in DirectVoxGO only");
     // shared memory map
     static constexpr int BLOB = W * KPAD * 2 + W * W * 2 + 16 * W * 2 + 2 * W * 16 * 2 + 16 * 16 * 2 + 128 * 16 * 2;
     static constexpr int BLOB_PAD = (BLOB + 1023) & ~1023;
@@ -47,7 +53,8 @@ struct TcCfg {
     static constexpr int WG_QW = WG_A;                       // float[384]
     static constexpr int WG_RACC = WG_QW + TC_RING * 4;      // float[128*3]
     static constexpr int WG_OWNER = WG_RACC + 128 * 3 * 4;   // u8[384]
-    static constexpr int WG_MISC = WG_OWNER + TC_RING;       // tail, tile slots, valid counts, exit flag, mbarriers
+    static constexpr int WG_QDIFF = WG_OWNER + TC_RING;      // float[384*3]: diffuse logits of the queued samples (!DIRECT only)
+    static constexpr int WG_MISC = WG_QDIFF + (DIRECT ? 0 : TC_RING * 3 * 4);   // tail, tile slots, valid counts, exit flag, mbarriers
     static constexpr int WG_BYTES = (WG_MISC + 128 + 1023) & ~1023;
     static constexpr int CTA_MISC = BLOB_PAD + 2 * WG_BYTES; // weight mbarrier, tmem slot, MLP action slots
     static constexpr int SMEM = CTA_MISC + 64;
@@ -241,6 +248,7 @@ k4_march_ws_kernel(const __grid_constant__ K4Dev s, const __grid_constant__ K4Re
         const uint32_t ring_s = s_u32(wg_base(g));
         const float* qw = reinterpret_cast<const float*>(wg_base(g) + Cfg::WG_QW);
         const unsigned char* qowner = wg_base(g) + Cfg::WG_OWNER;
+        const float* qdiff = reinterpret_cast<const float*>(wg_base(g) + Cfg::WG_QDIFF);
         float* racc = reinterpret_cast<float*>(wg_base(g) + Cfg::WG_RACC);
         const int bar_id = 3 + g;
         uint32_t full_ph = 0, mma_ph = 0;
@@ -301,8 +309,11 @@ k4_march_ws_kernel(const __grid_constant__ K4Dev s, const __grid_constant__ K4Re
                     const float wq = qw[slot];
                     const int owner = qowner[slot];
 #pragma unroll
-                    for (int ch = 0; ch < 3; ++ch)
-                        atomicAdd(racc + owner * 3 + ch, wq * sigmoid_ref(__uint_as_float(v[ch])));
+                    for (int ch = 0; ch < 3; ++ch) {
+                        float logit = __uint_as_float(v[ch]);
+                        if (!Cfg::DIRECT) logit = __fadd_rn(logit, qdiff[slot * 3 + ch]);      // rgb_logit + k0_diffuse
+                        atomicAdd(racc + owner * 3 + ch, wq * sigmoid_ref(logit));
+                    }
                 }
             }
             TC_FENCE_BEFORE();
@@ -320,6 +331,7 @@ k4_march_ws_kernel(const __grid_constant__ K4Dev s, const __grid_constant__ K4Re
         float* qw = reinterpret_cast<float*>(wgb + Cfg::WG_QW);
         float* racc = reinterpret_cast<float*>(wgb + Cfg::WG_RACC);
         unsigned char* qowner = wgb + Cfg::WG_OWNER;
+        float* qdiff = reinterpret_cast<float*>(wgb + Cfg::WG_QDIFF);
         WgCtl* ctl = wg_ctl(wg);
         volatile unsigned int* tailp = &ctl->tail;
         volatile long long* tile_slot = ctl->tile_slot;
@@ -482,8 +494,15 @@ k4_march_ws_kernel(const __grid_constant__ K4Dev s, const __grid_constant__ K4Re
                             const int mj = (int)roundf(__fmaf_rn(py, s.m_scale[1], s.m_shift[1]));
                             const int mk = (int)roundf(__fmaf_rn(pz, s.m_scale[2], s.m_shift[2]));
                             bool occ = false;
-                            if ((0 <= mi) & (mi < s.mX) & (0 <= mj) & (mj < s.mY) & (0 <= mk) & (mk < s.mZ))
-                                occ = __ldg(s.mask + ((size_t)mi * s.mY + mj) * s.mZ + mk) != 0;
+                            const bool in_mask = (0 <= mi) & (mi < s.mX) & (0 <= mj) & (mj < s.mY) & (0 <= mk) & (mk < s.mZ);
+                            if (in_mask) occ = __ldg(s.mask + ((size_t)mi * s.mY + mj) * s.mZ + mk) != 0;
+                            if (Cfg::KIND != K4_KIND_DCVGO && !occ && in_mask && s.skip) {
+                                // empty-space skipping: the following n steps are provably in-box and unoccupied
+                                const float h = (Cfg::KIND == K4_KIND_DVGO) ? rp.stepdist : __fdiv_rn(1.f, mpi_den);
+                                const int n = skip_steps(s, mi, mj, mk, r.sx, r.sy, r.sz, r.dx * h, r.dy * h, r.dz * h, i, r.n_steps);
+                                cnt_m += n;
+                                i += n;
+                            }
                             if (occ) {
                                 ++cnt_d;
                                 cell = make_cell(s, px, py, pz);
@@ -527,7 +546,7 @@ k4_march_ws_kernel(const __grid_constant__ K4Dev s, const __grid_constant__ K4Re
                         base = __shfl_sync(FULL, base, 0);
                         if (shade) {
                             const unsigned slot = (base + __popc(bal & ((1u << lane) - 1u))) % (unsigned)TC_RING;
-                            float f[Cfg::NS];
+                            float f[Cfg::NF];
                             interp_k0<Cfg::CPAD / 4>(s, cw, cidx, f);
                             if (Cfg::KIND == K4_KIND_DMPIGO) {
                                 const float pe[3] = {cell.cz, cell.cy, cell.cx};
@@ -541,10 +560,11 @@ k4_march_ws_kernel(const __grid_constant__ K4Dev s, const __grid_constant__ K4Re
                                         f[Cfg::C + 3 + 3 * Cfg::SPAPE + c * Cfg::SPAPE + q] = cosf(a);
                                     }
                             }
+                            if (Cfg::NS0 & 1) f[Cfg::K0OFF + Cfg::NS0] = 0.f;          // pad column of an odd feature count
                             uint32_t row[KPAD / 2];
 #pragma unroll
                             for (int j = 0; j < KPAD / 2; ++j) {
-                                if (j < Cfg::NS / 2) row[j] = pack2(f[2 * j], f[2 * j + 1]);
+                                if (j < Cfg::NS / 2) row[j] = pack2(f[Cfg::K0OFF + 2 * j], f[Cfg::K0OFF + 2 * j + 1]);
                                 else if (j < Cfg::NS / 2 + Cfg::NVW) row[j] = vw[j - Cfg::NS / 2];
                                 else row[j] = 0u;
                             }
@@ -555,6 +575,7 @@ k4_march_ws_kernel(const __grid_constant__ K4Dev s, const __grid_constant__ K4Re
                                     *reinterpret_cast<uint4*>(rowp + kc * 128) = make_uint4(row[4 * kc], row[4 * kc + 1], row[4 * kc + 2], row[4 * kc + 3]);
                             qw[slot] = w_sample;
                             qowner[slot] = (unsigned char)wt;
+                            if (!Cfg::DIRECT) { qdiff[slot * 3 + 0] = f[0]; qdiff[slot * 3 + 1] = f[1]; qdiff[slot * 3 + 2] = f[2]; }
                         }
                     }
                 }
@@ -631,24 +652,16 @@ int launch_ws(const k4_scene* sc, K4RenderParams rp, cudaStream_t st) {
     return K4_OK;
 }
 
-using CfgA = TcCfg<K4_KIND_DVGO, 12, 4, 0, 128>;    // configs/default.py:107-119 fine stage
-using CfgB = TcCfg<K4_KIND_DMPIGO, 9, 0, 0, 64>;    // configs/llff/llff_default_lg.py + fern_lg_joint_l1.py
-using CfgC = TcCfg<K4_KIND_DCVGO, 12, 4, 0, 128>;   // lib/dcvgo.py with the fine-stage colour net (same MLP as CfgA)
-
-template <class Cfg>
-bool matches(const K4Dev& v) {
-    return v.kind == Cfg::KIND && v.C == Cfg::C && v.viewpe == Cfg::VIEWPE && v.width == Cfg::W && v.depth == 3 &&
-           v.dim0 == Cfg::DIM0 && (Cfg::KIND == K4_KIND_DMPIGO ? v.spape == Cfg::SPAPE : v.direct != 0) &&
-           v.tc_blob != nullptr && v.tc_kpad == Cfg::KPAD;
-}
-
 }  // namespace
 
 int k4_launch_march_ws(const k4_scene* sc, K4RenderParams rp, cudaStream_t st) {
-    if (matches<CfgA>(sc->dev)) return launch_ws<CfgA>(sc, rp, st);
-    if (matches<CfgB>(sc->dev)) return launch_ws<CfgB>(sc, rp, st);
-    if (matches<CfgC>(sc->dev)) return launch_ws<CfgC>(sc, rp, st);
-    return K4_ERR_UNSUPPORTED;
+    if (!sc->dev.tc_blob) return K4_ERR_UNSUPPORTED;
+    switch (sc->dev.tc_cfg) {
+#define K4_X(id, kind, C, vpe, spe, W, direct) case id: return launch_ws<TcCfg<id, kind, C, vpe, spe, W, direct>>(sc, rp, st);
+        K4_WS_CFG_LIST(K4_X)
+#undef K4_X
+        default: return K4_ERR_UNSUPPORTED;
+    }
 }
 
-bool k4_ws_supported(const K4Dev& v) { return matches<CfgA>(v) || matches<CfgB>(v) || matches<CfgC>(v); }
+bool k4_ws_supported(const K4Dev& v) { return v.tc_blob != nullptr && v.tc_cfg >= 0; }

@@ -60,6 +60,8 @@ EXPORTS = {
     'k4_scene_create': (C.c_int, [C.POINTER(SceneDesc), C.c_void_p, C.POINTER(C.c_void_p)]),
     'k4_scene_destroy': (C.c_int, [C.c_void_p]),
     'k4_scene_device_bytes': (C.c_size_t, [C.c_void_p]),
+    'k4_scene_best_mlp_mode': (C.c_int, [C.c_void_p]),
+    'k4_scene_ws_config': (C.c_int, [C.c_void_p]),
     'k4_render_workspace_bytes': (C.c_size_t, [C.c_void_p, C.c_int64]),
     'k4_render_rays': (C.c_int, [C.c_void_p, C.POINTER(RenderArgs), C.c_void_p, C.c_void_p, C.c_void_p,
                                  C.c_int64, C.POINTER(RenderOut), C.c_void_p, C.c_size_t, C.c_void_p]),

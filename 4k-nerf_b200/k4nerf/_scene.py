@@ -170,21 +170,10 @@ class FusedRenderMixin:
         the fp32 oracle, profiles/r1_parity_all_modes.jsonl)."""
         if mode != 'auto':
             return mode
-        layers = linear_layers(self.rgbnet)
-        if not layers:
+        if not linear_layers(self.rgbnet):
             return 'fp32'
-        width, dim0 = layers[0].out_features, layers[0].in_features
-        C = self.k0.grid.shape[1]
-        vpe = int(getattr(self, 'viewbase_pe', 0))
-        spe = int(getattr(self, 'spatial_pe', 0))
-        if len(layers) == 3:
-            if self._k4_kind in (_lib.K4_KIND_DVGO, _lib.K4_KIND_DCVGO) and C == 12 and vpe == 4 and width == 128 and getattr(self, 'rgbnet_direct', True):
-                return 'ws'
-            if self._k4_kind == _lib.K4_KIND_DMPIGO and C == 9 and vpe == 0 and spe == 0 and width == 64:
-                return 'ws'
-            if width in (64, 128) and dim0 <= 64:
-                return 'f16'
-        return 'fp32'
+        best = _lib.lib.k4_scene_best_mlp_mode(self._get_scene().ptr)       # the library knows which shapes have a tcgen05 build
+        return {_lib.K4_MLP_TCGEN05_WS: 'ws', _lib.K4_MLP_F16: 'f16'}.get(best, 'fp32')
 
     def invalidate_scene(self):
         object.__setattr__(self, '_k4_handle', None)

@@ -138,6 +138,12 @@ K4_API int k4_device_check(void);                  /* K4_OK iff the current devi
 K4_API int k4_scene_create(const k4_scene_desc* desc, k4_stream_t stream, k4_scene** out_scene);
 K4_API int k4_scene_destroy(k4_scene* scene);
 K4_API size_t k4_scene_device_bytes(const k4_scene* scene);
+/* The fastest K4_MLP_* mode built for this scene's rgbnet shape: K4_MLP_TCGEN05_WS for every 3-layer MLP that one of
+ * the instantiated tcgen05 configurations covers (csrc/k4_ws_cfgs.h: k0 <= 16 channels, <= 6 view / <= 5 position
+ * frequencies, width <= 128, rgbnet_direct either way), else the mma.sync / fp32 kernels.  k4_scene_ws_config: the
+ * id of that configuration, -1 if none. */
+K4_API int k4_scene_best_mlp_mode(const k4_scene* scene);
+K4_API int k4_scene_ws_config(const k4_scene* scene);
 
 /* Scratch needed by k4_render_rays for n_rays (a few bytes of scheduler state). */
 K4_API size_t k4_render_workspace_bytes(const k4_scene* scene, int64_t n_rays);

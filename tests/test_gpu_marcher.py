@@ -185,3 +185,119 @@ def test_make_rays_matches_reference_formulas(cuda_device):
 
 # (the persistent multi-tile case lives in test_gpu_scale.py::test_persistent_multi_tile_vs_gpu_oracle, against the
 # reference kernels' pipeline instead of the repo's own mma.sync kernel)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# tcgen05 marcher for every shape the reference can produce (csrc/k4_ws_cfgs.h): exact instantiations and models that
+# run zero-padded on a larger instantiation.  `auto` must resolve to `ws` for all of them.
+# ---------------------------------------------------------------------------------------------------------------
+WS_SHAPES = [
+    # kind, scene kwargs, expected config id (k4_ws_cfgs.h)
+    ('cfgA', dict(k0_dim=12, viewbase_pe=0, width=128), 0),                       # configs/syn/1x_chair_joint_l1+gan.py
+    ('cfgA', dict(k0_dim=12, viewbase_pe=4, width=64), 3),
+    ('cfgA', dict(k0_dim=12, viewbase_pe=0, width=64), 2),
+    ('cfgA', dict(k0_dim=12, viewbase_pe=4, width=128, rgbnet_direct=False), 4),  # diffuse term, odd feature count (9)
+    ('cfgA', dict(k0_dim=15, viewbase_pe=4, width=128, rgbnet_direct=False), 4),
+    ('cfgA', dict(k0_dim=6, viewbase_pe=3, width=96), 1),                         # padded: fewer channels / frequencies / units
+    ('cfgA', dict(k0_dim=9, viewbase_pe=2, width=64), 3),
+    ('cfgA', dict(k0_dim=16, viewbase_pe=6, width=128), 5),
+    ('cfgA', dict(k0_dim=7, viewbase_pe=2, width=40, rgbnet_direct=False), 4),
+    ('cfgB', dict(k0_dim=12, viewbase_pe=4, spatial_pe=0, width=128), 7),
+    ('cfgB', dict(k0_dim=9, viewbase_pe=2, spatial_pe=3, width=64), 8),           # lib/dmpigo.py:96-100 position code
+    ('cfgB', dict(k0_dim=12, viewbase_pe=4, spatial_pe=5, width=128), 8),
+    ('cfgC', dict(k0_dim=12, viewbase_pe=0, width=128), 9),
+    ('cfgC', dict(k0_dim=8, viewbase_pe=2, width=64), 10),
+]
+
+
+@pytest.mark.parametrize('kind,skw,cfg_id', WS_SHAPES, ids=[f'{k}-{"-".join(f"{a}{b}" for a, b in v.items())}' for k, v, _ in WS_SHAPES])
+def test_tcgen05_marcher_covers_other_shapes(cuda_device, kind, skw, cfg_id):
+    from k4nerf import _lib
+    dev = cuda_device
+    if kind == 'cfgB':
+        st = make_state(kind, xy=40, depth=24, regime='fog', **skw)
+        hw = (24, 32)
+    else:
+        st = make_state(kind, res=40, regime='fog', **skw)
+        hw = (32, 40)
+    rays, kw = rays_for(st, *hw, **({'radius': 0.6} if kind == 'cfgC' else {}))
+    ro, rd, vd = rays
+    stats = {}
+    ref = pipeline.forward(st, ro, rd, vd, ops.CpuOps, stats=stats, **kw)
+    m = model_from_state(st, dev)
+    assert m.resolve_mlp_mode('auto') == 'ws'
+    assert _lib.lib.k4_scene_ws_config(m._get_scene().ptr) == cfg_id
+    n = ro.shape[0]
+    for img in (hw, None):
+        ours = m.render_rays(ro.to(dev), rd.to(dev), vd.to(dev), kw, image_hw=img, mlp_mode='auto', debug=True)
+        torch.cuda.synchronize()
+        check_geometry(ours, ref, stats, st, n)
+        cmp = compare(ours, ref, n)
+        assert cmp['rgb_marched_psnr'] >= PSNR_BAR['ws'], (skw, cmp)
+        assert cmp['alphainv_last_maxabs'] <= 2e-5, (skw, cmp)
+    # and against the exact-precision kernel on the same device
+    exact = m.render_rays(ro.to(dev), rd.to(dev), vd.to(dev), kw, mlp_mode='fp32')
+    assert torch.equal(exact['alphainv_last'], ours['alphainv_last'])
+    assert (exact['rgb_marched'] - ours['rgb_marched']).abs().max().item() < 5e-3
+
+
+def test_deeper_mlp_falls_back_to_exact_kernels(cuda_device):
+    """rgbnet_depth != 3 has no tensor-core build: auto must pick the fp32 kernel, not fail."""
+    st = make_state('cfgA', res=24, regime='fog', depth=4)
+    (ro, rd, vd), kw = rays_for(st, 12, 12)
+    m = model_from_state(st, cuda_device)
+    assert m.resolve_mlp_mode('auto') == 'fp32'
+    ref = pipeline.forward(st, ro, rd, vd, ops.CpuOps, **kw)
+    ours = m.render_rays(ro.to(cuda_device), rd.to(cuda_device), vd.to(cuda_device), kw)
+    assert compare(ours, ref, ro.shape[0])['rgb_marched_psnr'] >= 80.0
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# empty-space skipping is result preserving: same per-ray visit counts, depth, transmittance as the step-by-step walk
+# ---------------------------------------------------------------------------------------------------------------
+def _blob_state(kind, seed=0):
+    """Random sparse occupancy (blobs), density low outside: many skip / no-skip transitions along every ray."""
+    import torch.nn.functional as F
+    st = make_state('cfgB', xy=56, depth=40, regime='fog') if kind == 'cfgB' else make_state('cfgA', res=64, regime='fog')
+    g = torch.Generator().manual_seed(seed)
+    ws = list(st['density'].shape[2:])
+    seeds = (torch.rand(ws, generator=g) > 0.9985).float()[None, None]
+    blobs = F.max_pool3d(seeds, kernel_size=5, stride=1, padding=2)[0, 0] > 0
+    st['density'] = torch.where(blobs, torch.full(ws, 3.0), torch.full(ws, -6.0))[None, None].contiguous()
+    st['mask_cache'] = pipeline.mask_grid_state(blobs, st['xyz_min'], st['xyz_max'])
+    return st
+
+
+@pytest.mark.parametrize('kind,regime', [('cfgA', 'shell'), ('cfgA', 'blobs'), ('cfgA', 'fog'), ('cfgB', 'shell'), ('cfgB', 'blobs')])
+def test_empty_space_skipping_preserves_results(cuda_device, kind, regime, monkeypatch):
+    dev = cuda_device
+    if regime == 'blobs':
+        st = _blob_state(kind)
+    else:
+        st = make_state(kind, xy=56, depth=40, regime=regime) if kind == 'cfgB' else make_state(kind, res=64, regime=regime)
+    (ro, rd, vd), kw = rays_for(st, 96, 128)
+    ro, rd, vd = ro.to(dev), rd.to(dev), vd.to(dev)
+    stats = {}
+    ref = pipeline.forward(st, ro.cpu(), rd.cpu(), vd.cpu(), ops.CpuOps, stats=stats, **kw)
+    outs = {}
+    for skip in (True, False):
+        if skip:
+            monkeypatch.delenv('K4_NO_SKIP', raising=False)
+        else:
+            monkeypatch.setenv('K4_NO_SKIP', '1')          # read by k4_scene_create
+        m = model_from_state(st, dev)
+        for mode in ('ws', 'f16', 'fp32'):
+            for img in ((96, 128), None):
+                outs[(skip, mode, img)] = m.render_rays(ro, rd, vd, kw, image_hw=img, mlp_mode=mode, debug=True)
+        torch.cuda.synchronize()
+    for mode in ('ws', 'f16', 'fp32'):
+        for img in ((96, 128), None):
+            a, b = outs[(True, mode, img)], outs[(False, mode, img)]
+            assert torch.equal(a['ray_stats'], b['ray_stats']), (mode, img)
+            assert torch.equal(a['counters'][:3], b['counters'][:3]), (mode, img)
+            assert torch.equal(a['alphainv_last'], b['alphainv_last']) and torch.equal(a['depth'], b['depth']), (mode, img)
+            if mode == 'fp32':
+                assert torch.equal(a['rgb_marched'], b['rgb_marched'])
+            else:
+                assert (a['rgb_marched'] - b['rgb_marched']).abs().max().item() < 3e-5
+    check_geometry(outs[(True, 'ws', (96, 128))], ref, stats, st, ro.shape[0])
