@@ -118,7 +118,21 @@ struct ConvParams {
     // (y*out_s + out_oy, x*out_s + out_ox) of an (H*out_s) x (W*out_s) destination.  Defaults: 9 taps, out_s = 1.
     int ntaps; unsigned char tap_dy[9], tap_dx[9];
     int out_s, out_oy, out_ox;
+    // rows [y_lo, y_hi) of the iteration grid computed by this launch (all kernels; y_hi == 0 means all H rows): a unit
+    // of the multi-GPU decoder only needs, per layer, the rows inside the remaining receptive field of its kept block
+    int y_lo, y_hi;
+    float* dst_f2;                                                 // SRM_STORE_F32F16: second fp32 copy (the initial trunk)
+    // SRM_OUT_NCHW: output pixel (y, x) of channel c goes to out_nchw[c*out_ps + (y-crop_y0)*out_rs + (x-crop_x0)] when it lies
+    // in the crop window [crop_y0,crop_y1) x [crop_x0,crop_x1) (the kept block of a tile, written straight into the frame)
+    long long out_ps, out_rs; int crop_y0, crop_y1, crop_x0, crop_x1;
 };
+
+// Programmatic dependent launch: every decoder kernel is launched with programmaticStreamSerialization, so its CTAs are
+// scheduled while the previous kernel drains; the set-up above this point (barrier init, TMEM allocation, constant
+// weights) overlaps the predecessor's tail.  Nothing produced by an earlier kernel may be touched before the wait; the
+// dependents are released only after it, so at most two consecutive kernels are ever in flight.
+#define SR_PDL_SYNC() do { asm volatile("griddepcontrol.wait;\n" ::: "memory"); \
+                           asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory"); } while (0)
 
 template <int N>
 __global__ void __launch_bounds__(128) conv3x3_tc_kernel(const __grid_constant__ ConvParams p) {
@@ -132,7 +146,7 @@ __global__ void __launch_bounds__(128) conv3x3_tc_kernel(const __grid_constant__
     uint32_t* tslot = reinterpret_cast<uint32_t*>(smem + 2 * STAGE + 16);
     const int tid = threadIdx.x, warp = tid >> 5;
     const int ty = blockIdx.x / p.tiles_x, tx = blockIdx.x - ty * p.tiles_x;
-    const int y0 = ty * SR_TY, x0 = tx * SR_TX;
+    const int y0 = p.y_lo + ty * SR_TY, x0 = tx * SR_TX;
 
     if (tid == 0) {
         sr_mbar_init(mbar + 0, 1); sr_mbar_init(mbar + 1, 1);
@@ -146,6 +160,7 @@ __global__ void __launch_bounds__(128) conv3x3_tc_kernel(const __grid_constant__
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
     const uint32_t tbase = *tslot;
+    SR_PDL_SYNC();
 
     const int sH = p.upsample ? (p.H >> 1) : p.H, sW = p.upsample ? (p.W >> 1) : p.W;
     const int nchunks = p.cin / SR_CK;
@@ -215,7 +230,7 @@ __global__ void __launch_bounds__(128) conv3x3_tc_kernel(const __grid_constant__
 #pragma unroll 1
     for (int m = 0; m < SR_TM; ++m) {
     const int py = y0 + (tid >> 3), px = x0 + m * 8 + (tid & 7);
-    const bool inside = (py < p.H) & (px < p.W);
+    const bool inside = (py < p.y_hi) & (px < p.W);
     const size_t pix = (size_t)py * p.W + px;
 #pragma unroll
     for (int c16 = 0; c16 < NACC / 16; ++c16) {
@@ -261,10 +276,16 @@ __global__ void __launch_bounds__(128) conv3x3_tc_kernel(const __grid_constant__
             float4* d = reinterpret_cast<float4*>(p.dst_f + pix * 64 + c16 * 16);
 #pragma unroll
             for (int q = 0; q < 4; ++q) d[q] = make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+            if (p.dst_f2) {
+                float4* d2 = reinterpret_cast<float4*>(p.dst_f2 + pix * 64 + c16 * 16);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) d2[q] = make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+            }
         } else {  // SRM_OUT_NCHW
 #pragma unroll
             for (int j = 0; j < 16; ++j)
-                if (c16 * 16 + j < p.n_valid) p.out_nchw[(size_t)(c16 * 16 + j) * p.H * p.W + pix] = o[j];
+                if (c16 * 16 + j < p.n_valid && py >= p.crop_y0 && py < p.crop_y1 && px >= p.crop_x0 && px < p.crop_x1)
+                    p.out_nchw[(long long)(c16 * 16 + j) * p.out_ps + (long long)(py - p.crop_y0) * p.out_rs + (px - p.crop_x0)] = o[j];
         }
     }
     }
@@ -327,7 +348,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv3x3_ws_kernel(const __grid_
     const int tid = threadIdx.x, warp = tid >> 5;
     const int n_epi = p.use_tma ? 256 : 128;                                     // epilogue threads (8 or 4 warps)
     if (tid < 64) sbias[tid] = p.bias[tid];
-    const int tiles_x = (p.W + WS_TX - 1) / WS_TX, tiles_y = (p.H + SR_TY - 1) / SR_TY;
+    const int tiles_x = (p.W + WS_TX - 1) / WS_TX, tiles_y = (p.y_hi - p.y_lo + SR_TY - 1) / SR_TY;
     const int n_tiles = tiles_x * tiles_y;
     const int nchunks = p.cin / SR_CK;
 
@@ -345,6 +366,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv3x3_ws_kernel(const __grid_
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
     const uint32_t tbase = *tslot;
+    SR_PDL_SYNC();
 
     if (warp == 9) {
         // ------------------------------ producer (TMA): one thread, three bulk copies per stage ------------------------------
@@ -356,7 +378,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv3x3_ws_kernel(const __grid_
             const uint64_t tm = reinterpret_cast<uint64_t>(&tmap);
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
                 const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
-                const int y0 = ty * SR_TY - 1, x0 = tx * WS_TX - 1;
+                const int y0 = p.y_lo + ty * SR_TY - 1, x0 = tx * WS_TX - 1;
                 for (int c = 0; c < nchunks; ++c, ++g) {
                     const unsigned slot = g % C::NST;
                     if (g >= (unsigned)C::NST) sr_mbar_wait(empty + slot, ((g / C::NST) - 1) & 1);
@@ -384,7 +406,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv3x3_ws_kernel(const __grid_
         };
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
-            const int y0 = ty * SR_TY, x0 = tx * WS_TX;
+            const int y0 = p.y_lo + ty * SR_TY, x0 = tx * WS_TX;
             long long soff[WS_HALO_PER_THREAD];               // element offset of this thread's halo copies (-1: zero fill)
 #pragma unroll
             for (int j = 0; j < WS_HALO_PER_THREAD; ++j) {
@@ -471,15 +493,16 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv3x3_ws_kernel(const __grid_
         unsigned it = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
             const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
-            const int y0 = ty * SR_TY, x0 = tx * WS_TX;
+            const int y0 = p.y_lo + ty * SR_TY, x0 = tx * WS_TX;
             const unsigned a = it & 1;
             sr_mbar_wait(acc_full + a, (it >> 1) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
 #pragma unroll 1
             for (int m = m_lo; m < m_hi; ++m) {
                 const int py = y0 + (et >> 3), px = x0 + m * 8 + (et & 7);
-                const bool inside = (py < p.H) & (px < p.W);
-                const size_t pix = (size_t)(py * p.out_s + p.out_oy) * ((size_t)p.W * p.out_s) + (size_t)(px * p.out_s + p.out_ox);
+                const bool inside = (py < p.y_hi) & (px < p.W);
+                const int oy = py * p.out_s + p.out_oy, ox = px * p.out_s + p.out_ox;
+                const size_t pix = (size_t)oy * ((size_t)p.W * p.out_s) + (size_t)ox;
                 float4 res[NCH * 4];
                 if (has_res && inside) {
                     const float4* ad = reinterpret_cast<const float4*>(p.add_f + pix * 64);
@@ -529,10 +552,16 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv3x3_ws_kernel(const __grid_
                         float4* d = reinterpret_cast<float4*>(p.dst_f + pix * 64 + c16 * 16);
 #pragma unroll
                         for (int q = 0; q < 4; ++q) d[q] = make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
-                    } else {  // SRM_OUT_NCHW
+                        if (p.dst_f2) {
+                            float4* d2 = reinterpret_cast<float4*>(p.dst_f2 + pix * 64 + c16 * 16);
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) d2[q] = make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+                        }
+                    } else if (oy >= p.crop_y0 && oy < p.crop_y1 && ox >= p.crop_x0 && ox < p.crop_x1) {  // SRM_OUT_NCHW
 #pragma unroll
                         for (int j = 0; j < 16; ++j)
-                            if (c16 * 16 + j < p.n_valid) p.out_nchw[(size_t)(c16 * 16 + j) * p.H * p.W + pix] = o[j];
+                            if (c16 * 16 + j < p.n_valid)
+                                p.out_nchw[(long long)(c16 * 16 + j) * p.out_ps + (long long)(oy - p.crop_y0) * p.out_rs + (ox - p.crop_x0)] = o[j];
                     }
                 }
             }
@@ -594,7 +623,7 @@ __global__ void __launch_bounds__(K64_THREADS, 1) conv3x3_k64_kernel(const __gri
     float* sbias = reinterpret_cast<float*>(Ar + C::NST * K64_A_STAGE + 256);   // [64]
     const int tid = threadIdx.x, warp = tid >> 5;
     if (tid < 64) sbias[tid] = p.bias[tid];
-    const int tiles_x = (p.W + K64_TX - 1) / K64_TX, tiles_y = (p.H + SR_TY - 1) / SR_TY;
+    const int tiles_x = (p.W + K64_TX - 1) / K64_TX, tiles_y = (p.y_hi - p.y_lo + SR_TY - 1) / SR_TY;
     const int n_tiles = tiles_x * tiles_y;
 
     if (tid == 0) {
@@ -621,6 +650,7 @@ __global__ void __launch_bounds__(K64_THREADS, 1) conv3x3_k64_kernel(const __gri
             for (int t = 0; t < p.ntaps; ++t)
                 asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n"
                              :: "r"(sr_s32(Bw + t * C::B_TAP)), "l"(tb), "r"(sr_s32(wbar)), "r"(0), "r"(t * N) : "memory");
+            SR_PDL_SYNC();                                        // the weights above are constants; the activations are not
             unsigned g = 0;
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++g) {
                 const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
@@ -629,7 +659,7 @@ __global__ void __launch_bounds__(K64_THREADS, 1) conv3x3_k64_kernel(const __gri
                 const uint32_t bar = sr_s32(full + slot);
                 asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" :: "r"(bar), "r"((uint32_t)K64_A_BYTES) : "memory");
                 asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n"
-                             :: "r"(sr_s32(Ar + slot * K64_A_STAGE)), "l"(ta), "r"(bar), "r"(0), "r"(tx * K64_TX - 1), "r"(ty * SR_TY - 1) : "memory");
+                             :: "r"(sr_s32(Ar + slot * K64_A_STAGE)), "l"(ta), "r"(bar), "r"(0), "r"(tx * K64_TX - 1), "r"(p.y_lo + ty * SR_TY - 1) : "memory");
             }
         }
     } else if (warp == 8) {
@@ -664,6 +694,7 @@ __global__ void __launch_bounds__(K64_THREADS, 1) conv3x3_k64_kernel(const __gri
         }
     } else {
         // ------------------------------ epilogue: 8 warps, thread = pixel, work items (m, 16-column block) dealt to the two groups ------------------------------
+        SR_PDL_SYNC();                                            // residual reads / output writes touch earlier kernels' buffers
         constexpr int NCH = C::NACC / 16;
         constexpr int ITEMS = K64_TM * NCH;                     // 12 (N = 64) or 3 (N = 16)
         const int et = tid & 127, egrp = tid >> 7;
@@ -672,7 +703,7 @@ __global__ void __launch_bounds__(K64_THREADS, 1) conv3x3_k64_kernel(const __gri
         unsigned g = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++g) {
             const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
-            const int y0 = ty * SR_TY, x0 = tx * K64_TX;
+            const int y0 = p.y_lo + ty * SR_TY, x0 = tx * K64_TX;
             const unsigned a = g & 1;
             sr_mbar_wait(acc_full + a, (g >> 1) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
@@ -680,14 +711,15 @@ __global__ void __launch_bounds__(K64_THREADS, 1) conv3x3_k64_kernel(const __gri
             for (int it0 = egrp; it0 < ITEMS; it0 += 4) {        // two items of this group per round: it0 and it0 + 2
                 uint32_t v[2][16];
                 float4 res[2][4];
-                bool ins[2]; size_t opix[2]; int c16s[2];
+                bool ins[2]; size_t opix[2]; int c16s[2]; int oys[2], oxs[2];
 #pragma unroll
                 for (int u = 0; u < 2; ++u) {
                     const int it = it0 + 2 * u;
                     const int m = (it < ITEMS) ? it / NCH : 0, c16 = (it < ITEMS) ? it % NCH : 0;
                     const int py = y0 + (et >> 3), px = x0 + m * 8 + (et & 7);
-                    ins[u] = (it < ITEMS) & (py < p.H) & (px < p.W);
-                    opix[u] = (size_t)(py * p.out_s + p.out_oy) * ((size_t)p.W * p.out_s) + (size_t)(px * p.out_s + p.out_ox);
+                    ins[u] = (it < ITEMS) & (py < p.y_hi) & (px < p.W);
+                    oys[u] = py * p.out_s + p.out_oy; oxs[u] = px * p.out_s + p.out_ox;
+                    opix[u] = (size_t)oys[u] * ((size_t)p.W * p.out_s) + (size_t)oxs[u];
                     c16s[u] = c16;
                     if (has_res && ins[u]) {
                         const float4* ad = reinterpret_cast<const float4*>(p.add_f + opix[u] * 64 + c16 * 16);
@@ -727,10 +759,11 @@ __global__ void __launch_bounds__(K64_THREADS, 1) conv3x3_k64_kernel(const __gri
                         uint4* d = reinterpret_cast<uint4*>(p.dst_h + pix * p.dst_cstride + p.dst_c0 + c16 * 16);
                         d[0] = *reinterpret_cast<uint4*>(&h[0]);
                         d[1] = *reinterpret_cast<uint4*>(&h[4]);
-                    } else {  // SRM_OUT_NCHW
+                    } else if (oys[u] >= p.crop_y0 && oys[u] < p.crop_y1 && oxs[u] >= p.crop_x0 && oxs[u] < p.crop_x1) {  // SRM_OUT_NCHW
 #pragma unroll
                         for (int j = 0; j < 16; ++j)
-                            if (c16 * 16 + j < p.n_valid) p.out_nchw[(size_t)(c16 * 16 + j) * p.H * p.W + pix] = o[j];
+                            if (c16 * 16 + j < p.n_valid)
+                                p.out_nchw[(long long)(c16 * 16 + j) * p.out_ps + (long long)(oys[u] - p.crop_y0) * p.out_rs + (oxs[u] - p.crop_x0)] = o[j];
                     }
                 }
             }
@@ -752,7 +785,8 @@ struct SftParams {
     const float* x_f; const __half* x_h; int xh_cstride, xh_c0;     // input: fp32 [P,64] or fp16 channel range
     __half* dst_h; int dst_cstride, dst_c0;                          // fp16 output (or nullptr)
     float* dst_f; const float* res_f; float res_scale;               // fp32 output: y*res_scale + res_f (RRDB tail) when dst_f != nullptr
-    long long P;
+    long long P;                                                     // pixels processed ...
+    long long p0;                                                    // ... starting at this pixel (row window of a decoder unit)
 };
 
 template <int COUT>
@@ -765,8 +799,9 @@ __global__ void __launch_bounds__(128) sft_kernel(const __grid_constant__ SftPar
     const float* h0 = s0b + 32;       const float* h0b = h0 + 1024;
     const float* s1 = h0b + 32;       const float* s1b = s1 + COUT * 32;
     const float* h1 = s1b + COUT;     const float* h1b = h1 + COUT * 32;
-    const long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (pix >= p.P) return;
+    const long long lp = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (lp >= p.P) return;
+    const long long pix = p.p0 + lp;
     float c[32], ts[32], th[32];
     const float4* cp = reinterpret_cast<const float4*>(p.cond + pix * 32);
 #pragma unroll
@@ -854,7 +889,7 @@ struct SftTcParams {
     const float* x_f; const __half* x_h; int xh_cstride, xh_c0;
     __half* dst_h; int dst_cstride, dst_c0;
     float* dst_f; const float* res_f; float res_scale;
-    long long P; int n_tiles;
+    long long P; long long p0; int n_tiles;
 };
 
 template <int COUT>
@@ -886,6 +921,7 @@ __global__ void __launch_bounds__(128, (COUT == 64) ? 2 : 4) sft_tc_kernel(const
     const uint32_t tl = tbase + ((uint32_t)(warp * 32) << 16);
     const uint32_t blob_s = sr_s32(blob), a_s = sr_s32(atile);
     uint32_t ph = 0;
+    SR_PDL_SYNC();
 
     // Register software pipeline: the kernel is a chain of dependent phases per 128-pixel tile (cond -> GEMM 1 ->
     // repack -> GEMM 2 -> modulate) with only 8-16 warps per SM, so every global load that is issued where it is
@@ -894,14 +930,14 @@ __global__ void __launch_bounds__(128, (COUT == 64) ? 2 : 4) sft_tc_kernel(const
     float4 cnd[8];
     auto load_cond = [&](int t) {
         const long long px_ = (long long)t * 128 + tid;
-        const float4* cp = reinterpret_cast<const float4*>(p.cond + (px_ < p.P ? px_ : 0) * 32);
+        const float4* cp = reinterpret_cast<const float4*>(p.cond + (p.p0 + (px_ < p.P ? px_ : 0)) * 32);
 #pragma unroll
         for (int k = 0; k < 8; ++k) cnd[k] = __ldg(cp + k);
     };
     if ((int)blockIdx.x < p.n_tiles) load_cond(blockIdx.x);
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-        const long long pix = (long long)tile * 128 + tid;
-        const bool valid = pix < p.P;
+        const bool valid = (long long)tile * 128 + tid < p.P;
+        const long long pix = p.p0 + (long long)tile * 128 + tid;
         // cond row -> fp16, canonical layout (row = tid, 4 chunks of 8 channels)
 #pragma unroll
         for (int kc = 0; kc < 4; ++kc) {
@@ -1035,7 +1071,7 @@ __global__ void pack_sft_blob_kernel(const float* __restrict__ w, unsigned char*
 }
 
 // CondNet: conv3x3(1->64) lrelu, 1x1 64->64 lrelu, 1x1 64->64 lrelu, 1x1 64->32   (lib/sr_esrnet.py:440-444)
-struct CondParams { const float* cond_in; const float* w; float* cond_out; int H, W; };   // w: c0 [64][9], b0[64], c2 [64][64], b2, c4 [64][64], b4, c6 [32][64], b6
+struct CondParams { const float* cond_in; const float* w; float* cond_out; int H, W; int y_lo, y_hi; };   // w: c0 [64][9], b0[64], c2 [64][64], b2, c4 [64][64], b4, c6 [32][64], b6
 
 __global__ void __launch_bounds__(128) condnet_kernel(const __grid_constant__ CondParams p) {
     constexpr int NW = 64 * 9 + 64 + 2 * (64 * 64 + 64) + 32 * 64 + 32;
@@ -1044,8 +1080,9 @@ __global__ void __launch_bounds__(128) condnet_kernel(const __grid_constant__ Co
     __syncthreads();
     const float* c0 = sw; const float* b0 = c0 + 576; const float* c2 = b0 + 64; const float* b2 = c2 + 4096;
     const float* c4 = b2 + 64; const float* b4 = c4 + 4096; const float* c6 = b4 + 64; const float* b6 = c6 + 2048;
-    const long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (pix >= (long long)p.H * p.W) return;
+    SR_PDL_SYNC();
+    const long long pix = (long long)p.y_lo * p.W + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pix >= (long long)p.y_hi * p.W) return;
     const int y = (int)(pix / p.W), x = (int)(pix - (long long)y * p.W);
     float n[9];
 #pragma unroll
@@ -1088,6 +1125,7 @@ __global__ void __launch_bounds__(128) condnet_kernel(const __grid_constant__ Co
 
 // planar fp32 [C,H,W] -> NHWC fp16 [H,W,32] (zero padded)
 __global__ void nchw_to_nhwc32_kernel(const float* __restrict__ src, __half* __restrict__ dst, int C, long long P) {
+    SR_PDL_SYNC();
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P * 32) return;
     const long long pix = i >> 5;
@@ -1270,18 +1308,51 @@ int make_sft(k4_srnet* n, SrSft& f, const float* const* pw, int cout, cudaStream
     return K4_OK;
 }
 
+// K4_SR_PDL=0 launches the decoder kernels without programmatic dependent launch (A/B switch)
+static bool sr_use_pdl() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("K4_SR_PDL"); v = (e && e[0] == '0') ? 0 : 1; }
+    return v == 1;
+}
+
+template <typename... KArgs, typename... Args>
+cudaError_t sr_launch(void (*kern)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t s, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = sr_use_pdl() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
+// per-device caches of the launchers (function attributes are per device)
+struct SrDevInfo { int sms; unsigned attr_mask; };
+static SrDevInfo* sr_dev() {
+    static SrDevInfo info[64];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+    if (info[dev].sms == 0) cudaDeviceGetAttribute(&info[dev].sms, cudaDevAttrMultiProcessorCount, dev);
+    return &info[dev];
+}
+template <typename F>
+int sr_set_smem(F kern, int bit, int bytes) {
+    SrDevInfo* d = sr_dev();
+    if (!(d->attr_mask & (1u << bit))) {
+        K4_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+        d->attr_mask |= (1u << bit);
+    }
+    return K4_OK;
+}
+constexpr int sr_bit_n(int n) { return n == 64 ? 0 : (n == 32 ? 1 : 2); }
+
 template <int N>
 int launch_conv(const ConvParams& p, cudaStream_t s) {
     constexpr int STAGE = SR_A_STAGE + 9 * N * SR_CK * 2;
     constexpr int SMEM = 2 * STAGE + 64;
-    static bool attr_set = false;
-    if (!attr_set) {
-        K4_CUDA_TRY(cudaFuncSetAttribute(conv3x3_tc_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-        attr_set = true;
-    }
-    const int tiles_y = (p.H + SR_TY - 1) / SR_TY;
-    conv3x3_tc_kernel<N><<<(unsigned)(p.tiles_x * tiles_y), 128, SMEM, s>>>(p);
-    K4_CUDA_TRY(cudaGetLastError());
+    if (int st = sr_set_smem(conv3x3_tc_kernel<N>, 0 + sr_bit_n(N), SMEM)) return st;
+    const int tiles_y = (p.y_hi - p.y_lo + SR_TY - 1) / SR_TY;
+    K4_CUDA_TRY(sr_launch(conv3x3_tc_kernel<N>, (unsigned)(p.tiles_x * tiles_y), 128, SMEM, s, p));
     return K4_OK;
 }
 
@@ -1328,21 +1399,14 @@ static bool sr_no_tma() {
 template <int N>
 int launch_conv_ws(ConvParams p, cudaStream_t s) {
     using C = WsCfg<N>;
-    static bool attr_set = false;
-    static int sms = 0;
-    if (!attr_set) {
-        K4_CUDA_TRY(cudaFuncSetAttribute(conv3x3_ws_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
-        int dev = 0;
-        K4_CUDA_TRY(cudaGetDevice(&dev));
-        K4_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-        attr_set = true;
-    }
+    if (int st = sr_set_smem(conv3x3_ws_kernel<N>, 3 + sr_bit_n(N), C::SMEM)) return st;
+    const int sms = sr_dev()->sms;
     alignas(64) CUtensorMap tm;
     memset(&tm, 0, sizeof(tm));
     p.use_tma = (!p.upsample && !sr_no_tma() && sr_make_tmap(p, &tm)) ? 1 : 0;
-    const int tiles = ((p.W + WS_TX - 1) / WS_TX) * ((p.H + SR_TY - 1) / SR_TY);
-    conv3x3_ws_kernel<N><<<(unsigned)(tiles < sms ? tiles : sms), WS_THREADS, C::SMEM, s>>>(p, tm);
-    K4_CUDA_TRY(cudaGetLastError());
+    const int tiles = ((p.W + WS_TX - 1) / WS_TX) * ((p.y_hi - p.y_lo + SR_TY - 1) / SR_TY);
+    if (tiles <= 0) return K4_OK;
+    K4_CUDA_TRY(sr_launch(conv3x3_ws_kernel<N>, (unsigned)(tiles < sms ? tiles : sms), WS_THREADS, C::SMEM, s, p, tm));
     return K4_OK;
 }
 
@@ -1350,17 +1414,10 @@ int launch_conv_ws(ConvParams p, cudaStream_t s) {
 template <int N>
 int launch_conv_k64(ConvParams p, const __half* wrows, cudaStream_t s) {
     using C = K64Cfg<N>;
-    static bool attr_set = false;
-    static int sms = 0;
     k4_encode_tiled_fn enc = sr_encode_tiled();
     if (!enc) return K4_ERR_UNSUPPORTED;
-    if (!attr_set) {
-        K4_CUDA_TRY(cudaFuncSetAttribute(conv3x3_k64_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
-        int dev = 0;
-        K4_CUDA_TRY(cudaGetDevice(&dev));
-        K4_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-        attr_set = true;
-    }
+    if (int st = sr_set_smem(conv3x3_k64_kernel<N>, 6 + sr_bit_n(N), C::SMEM)) return st;
+    const int sms = sr_dev()->sms;
     alignas(64) CUtensorMap ta, tb;
     {
         const cuuint64_t gdim[3] = {64, (cuuint64_t)p.W, (cuuint64_t)p.H};
@@ -1378,9 +1435,9 @@ int launch_conv_k64(ConvParams p, const __half* wrows, cudaStream_t s) {
                 CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
             return K4_ERR_UNSUPPORTED;
     }
-    const int tiles = ((p.W + K64_TX - 1) / K64_TX) * ((p.H + SR_TY - 1) / SR_TY);
-    conv3x3_k64_kernel<N><<<(unsigned)(tiles < sms ? tiles : sms), K64_THREADS, C::SMEM, s>>>(p, ta, tb);
-    K4_CUDA_TRY(cudaGetLastError());
+    const int tiles = ((p.W + K64_TX - 1) / K64_TX) * ((p.y_hi - p.y_lo + SR_TY - 1) / SR_TY);
+    if (tiles <= 0) return K4_OK;
+    K4_CUDA_TRY(sr_launch(conv3x3_k64_kernel<N>, (unsigned)(tiles < sms ? tiles : sms), K64_THREADS, C::SMEM, s, p, ta, tb));
     return K4_OK;
 }
 
@@ -1407,6 +1464,10 @@ int run_conv(const SrConv& c, ConvParams p, cudaStream_t s, const __half* wk64_o
         for (int t = 0; t < 9; ++t) { p.tap_dy[t] = (unsigned char)(t / 3); p.tap_dx[t] = (unsigned char)(t % 3); }
     }
     if (p.out_s == 0) p.out_s = 1;
+    if (p.y_hi == 0) { p.y_lo = 0; p.y_hi = p.H; }
+    if (p.y_lo < 0) p.y_lo = 0;
+    if (p.y_hi > p.H) p.y_hi = p.H;
+    if (p.y_hi <= p.y_lo) return K4_OK;
     p.tiles_x = (p.W + SR_TX - 1) / SR_TX;
     if (sr_use_v1()) {
         if (c.npad == 64) return launch_conv<64>(p, s);
@@ -1454,17 +1515,12 @@ int launch_sft_tc(const SftTcParams& p, cudaStream_t s) {
     // TMEM budget would otherwise sit in tcgen05.alloc until a neighbour exits
     int smem = ((BL.total + 1023) & ~1023) + 8192 + 64;
     if (smem < (200 * 1024) / per_sm_c) smem = (200 * 1024) / per_sm_c;
-    static int sms = 0;
-    if (!sms) {
-        int dev = 0;
-        K4_CUDA_TRY(cudaGetDevice(&dev));
-        K4_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-        K4_CUDA_TRY(cudaFuncSetAttribute(sft_tc_kernel<COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    }
+    if (int st = sr_set_smem(sft_tc_kernel<COUT>, 9 + (COUT == 64 ? 0 : 1), smem)) return st;
+    const int sms = sr_dev()->sms;
     const int per_sm = per_sm_c;
+    if (p.n_tiles <= 0) return K4_OK;
     int grid = p.n_tiles < sms * per_sm ? p.n_tiles : sms * per_sm;
-    sft_tc_kernel<COUT><<<grid, 128, smem, s>>>(p);
-    K4_CUDA_TRY(cudaGetLastError());
+    K4_CUDA_TRY(sr_launch(sft_tc_kernel<COUT>, (unsigned)grid, 128, (size_t)smem, s, p));
     return K4_OK;
 }
 
@@ -1477,7 +1533,7 @@ int run_sft(const SrSft& f, SftParams p, cudaStream_t s) {
     SftTcParams q{};
     q.cond = p.cond; q.blob = f.blob; q.x_f = p.x_f; q.x_h = p.x_h; q.xh_cstride = p.xh_cstride; q.xh_c0 = p.xh_c0;
     q.dst_h = p.dst_h; q.dst_cstride = p.dst_cstride; q.dst_c0 = p.dst_c0; q.dst_f = p.dst_f; q.res_f = p.res_f;
-    q.res_scale = p.res_scale; q.P = p.P; q.n_tiles = (int)((p.P + 127) / 128);
+    q.res_scale = p.res_scale; q.P = p.P; q.p0 = p.p0; q.n_tiles = (int)((p.P + 127) / 128);
     return f.cout == 64 ? launch_sft_tc<64>(q, s) : launch_sft_tc<32>(q, s);
 }
 
@@ -1559,9 +1615,19 @@ extern "C" size_t k4_srnet_workspace_bytes(const k4_srnet*, int32_t h, int32_t w
     return sr_ws(h, w).total;
 }
 
-extern "C" int k4_srnet_forward(const k4_srnet* n, const float* d_x, const float* d_cond, int32_t h, int32_t w,
-                                float* d_out, void* d_ws, size_t ws_bytes, k4_stream_t stream) {
+// Rows [lo, hi) of an h-row tile that a layer must produce when `r` more rows of receptive field follow it
+// (keep rows [ky0, ky1)); clipped to the tile -- beyond it the convolutions see their zero padding.
+struct SrRows { int lo, hi; };
+static inline SrRows sr_rows(int ky0, int ky1, int r, int h) {
+    SrRows o; o.lo = ky0 - r < 0 ? 0 : ky0 - r; o.hi = ky1 + r > h ? h : ky1 + r; return o;
+}
+
+extern "C" int k4_srnet_forward_roi(const k4_srnet* n, const float* d_x, const float* d_cond, int32_t h, int32_t w,
+                                    int32_t keep_y0, int32_t keep_y1, int32_t keep_x0, int32_t keep_x1,
+                                    float* d_out, int64_t out_plane_stride, int64_t out_row_stride,
+                                    void* d_ws, size_t ws_bytes, k4_stream_t stream) {
     if (!n || !d_x || !d_cond || !d_out || h <= 0 || w <= 0) return K4_ERR_INVALID_ARG;
+    if (keep_y0 < 0 || keep_y1 > h || keep_y0 >= keep_y1 || keep_x0 < 0 || keep_x1 > w || keep_x0 >= keep_x1) return K4_ERR_INVALID_ARG;
     const SrWs L = sr_ws(h, w);
     if (!d_ws || ws_bytes < L.total) return K4_ERR_WORKSPACE;
     cudaStream_t s = (cudaStream_t)stream;
@@ -1571,80 +1637,110 @@ extern "C" int k4_srnet_forward(const k4_srnet* n, const float* d_x, const float
     float* tA = (float*)(ws + L.trunkA); float* tB = (float*)(ws + L.trunkB); __half* cat = (__half*)(ws + L.cat);
     __half* sbody = (__half*)(ws + L.sbody); __half* bf = (__half*)(ws + L.bf);
     __half* up1 = (__half*)(ws + L.up1); __half* up2 = (__half*)(ws + L.up2); __half* hr = (__half*)(ws + L.hr);
+    const int ky0 = keep_y0, ky1 = keep_y1;
+    // Remaining receptive radius (LR rows) behind each layer, from the output backwards: conv_last / conv_hr / up2 / up1
+    // need 1/4 + 1/4 + 1/4 + 1/2 LR rows (handled exactly in high-resolution rows below), conv_body 1, every 3x3 conv of a
+    // residual dense block 1 (SFT layers 0), conv_first 1: the trunk entering conv_body's SFT is needed on rows(3), the
+    // output of the k-th dense block from the end on rows(3 + 5k), conv_first's on rows(3 + 5 * 3 * num_block).
+    const int nrdb = 3 * n->num_block;
     int st;
 #define SR_DO(x) do { st = (x); if (st != K4_OK) return st; } while (0)
-    nchw_to_nhwc32_kernel<<<(unsigned)((P * 32 + 255) / 256), 256, 0, s>>>(d_x, in16, 3, P);
-    K4_CUDA_TRY(cudaGetLastError());
+    K4_CUDA_TRY(sr_launch(nchw_to_nhwc32_kernel, (unsigned)((P * 32 + 255) / 256), 256, 0, s, d_x, in16, 3, P));
     {
-        CondParams cp{d_cond, n->condnet_w, cond32, h, w};
+        const SrRows rr = sr_rows(ky0, ky1, 3 + 5 * nrdb + 5, h);          // every SFT layer inside the window reads it
+        CondParams cp{d_cond, n->condnet_w, cond32, h, w, rr.lo, rr.hi};
         constexpr int NW = 64 * 9 + 64 + 2 * (64 * 64 + 64) + 32 * 64 + 32;
-        static bool set = false;
-        if (!set) { K4_CUDA_TRY(cudaFuncSetAttribute(condnet_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, NW * 4)); set = true; }
-        condnet_kernel<<<(unsigned)((P + 127) / 128), 128, NW * 4, s>>>(cp);
-        K4_CUDA_TRY(cudaGetLastError());
+        SR_DO(sr_set_smem(condnet_kernel, 11, NW * 4));
+        const long long np = (long long)(rr.hi - rr.lo) * w;
+        K4_CUDA_TRY(sr_launch(condnet_kernel, (unsigned)((np + 127) / 128), 128, (size_t)NW * 4, s, cp));
     }
     ConvParams c0{};
     c0.H = h; c0.W = w;
-    {   // feat = conv_first(x): fp32 into `feat`, copy = initial trunk
-        ConvParams p = c0; p.src = in16; p.src_cstride = 32; p.src_c0 = 0; p.mode = SRM_STORE_F32F16; p.dst_f = feat;
+    auto rows = [&](ConvParams& p, int r) { const SrRows q = sr_rows(ky0, ky1, r, h); p.y_lo = q.lo; p.y_hi = q.hi; };
+    auto win = [&](SftParams& sp, int r) { const SrRows q = sr_rows(ky0, ky1, r, h); sp.p0 = (long long)q.lo * w; sp.P = (long long)(q.hi - q.lo) * w; };
+    {   // feat = conv_first(x): fp32 into `feat` and into trunk A (the initial trunk)
+        ConvParams p = c0; p.src = in16; p.src_cstride = 32; p.src_c0 = 0; p.mode = SRM_STORE_F32F16; p.dst_f = feat; p.dst_f2 = tA;
+        rows(p, 3 + 5 * nrdb);
         SR_DO(run_conv(n->conv_first, p, s));
-        K4_CUDA_TRY(cudaMemcpyAsync(tA, feat, (size_t)P * 64 * 4, cudaMemcpyDeviceToDevice, s));
     }
     for (int i = 0; i < n->num_block; ++i) {
         // RRDB_SFT.forward: trunk A holds x (kept for the block's tail), RDBs update A -> B -> B -> B
         const float* cur = tA;
         for (int j = 0; j < 3; ++j) {
+            const int k = nrdb - 1 - (3 * i + j);                              // dense blocks still to come
+            const int base = 3 + 5 * k;                                        // rows(base): this block's output
             {   // xc0 = sft0(x) -> cat[0:64]
-                SftParams sp{}; sp.cond = cond32; sp.x_f = cur; sp.dst_h = cat; sp.dst_cstride = 192; sp.dst_c0 = 0; sp.P = P;
+                SftParams sp{}; sp.cond = cond32; sp.x_f = cur; sp.dst_h = cat; sp.dst_cstride = 192; sp.dst_c0 = 0;
+                win(sp, base + 5);
                 SR_DO(run_sft(n->rdb_sft[i][j][0], sp, s));
             }
             for (int c = 0; c < 4; ++c) {   // x{c+1} = lrelu(conv(cat[0:64+32c])) -> cat[64+32c : 96+32c]
                 ConvParams p = c0; p.src = cat; p.src_cstride = 192; p.src_c0 = 0; p.mode = SRM_STORE_F16; p.lrelu = 0.2f;
                 p.dst_h = cat; p.dst_cstride = 192; p.dst_c0 = 64 + 32 * c;
+                rows(p, base + 4 - c);
                 SR_DO(run_conv(n->rdb_conv[i][j][c], p, s));
             }
             {   // xc1 = sft1(x4) in place: cat[160:192]
                 SftParams sp{}; sp.cond = cond32; sp.x_h = cat; sp.xh_cstride = 192; sp.xh_c0 = 160;
-                sp.dst_h = cat; sp.dst_cstride = 192; sp.dst_c0 = 160; sp.P = P;
+                sp.dst_h = cat; sp.dst_cstride = 192; sp.dst_c0 = 160;
+                win(sp, base + 1);
                 SR_DO(run_sft(n->rdb_sft[i][j][1], sp, s));
             }
             {   // x = conv5(cat) * 0.2 + x
                 ConvParams p = c0; p.src = cat; p.src_cstride = 192; p.src_c0 = 0; p.mode = SRM_TRUNK; p.scale = 0.2f;
                 p.add_f = cur; p.dst_f = tB;
+                rows(p, base);
                 SR_DO(run_conv(n->rdb_conv[i][j][4], p, s));
                 cur = tB;
             }
         }
         {   // out = sft0(rdb3 out) * 0.2 + x_in  -> A
-            SftParams sp{}; sp.cond = cond32; sp.x_f = tB; sp.dst_f = tA; sp.res_f = tA; sp.res_scale = 0.2f; sp.P = P;
+            SftParams sp{}; sp.cond = cond32; sp.x_f = tB; sp.dst_f = tA; sp.res_f = tA; sp.res_scale = 0.2f;
+            win(sp, 3 + 5 * (nrdb - 3 * (i + 1)));
             SR_DO(run_sft(n->rrdb_sft[i], sp, s));
         }
     }
     {   // body_feat = conv_body(sftbody(trunk)) + feat
-        SftParams sp{}; sp.cond = cond32; sp.x_f = tA; sp.dst_h = sbody; sp.dst_cstride = 64; sp.dst_c0 = 0; sp.P = P;
+        SftParams sp{}; sp.cond = cond32; sp.x_f = tA; sp.dst_h = sbody; sp.dst_cstride = 64; sp.dst_c0 = 0;
+        win(sp, 3);
         SR_DO(run_sft(n->sftbody, sp, s));
         ConvParams p = c0; p.src = sbody; p.src_cstride = 64; p.mode = SRM_ADD_STORE_F16; p.add_f = feat; p.dst_h = bf; p.dst_cstride = 64;
+        rows(p, 2);
         SR_DO(run_conv(n->conv_body, p, s));
     }
-    {   // upsample x2 (nearest) + conv + lrelu, twice; conv_hr + lrelu; conv_last
+    {   // upsample x2 (nearest) + conv + lrelu, twice; conv_hr + lrelu; conv_last (rows in the layer's own resolution)
         ConvParams p = c0; p.H = 2 * h; p.W = 2 * w; p.upsample = 1; p.src = bf; p.src_cstride = 64; p.mode = SRM_STORE_F16; p.lrelu = 0.2f;
         p.dst_h = up1; p.dst_cstride = 64;
+        auto clip = [](int v, int hi) { return v < 0 ? 0 : (v > hi ? hi : v); };
         if (sr_use_v1()) {
+            p.y_lo = clip(2 * ky0 - 2, 2 * h); p.y_hi = clip(2 * ky1 + 2, 2 * h);
             SR_DO(run_conv(n->conv_up1, p, s));
             p.H = 4 * h; p.W = 4 * w; p.src = up1; p.dst_h = up2;
+            p.y_lo = clip(4 * ky0 - 2, 4 * h); p.y_hi = clip(4 * ky1 + 2, 4 * h);
             SR_DO(run_conv(n->conv_up2, p, s));
         } else {
             p.H = h; p.W = w;                                   // iterate over the SOURCE grid, write the 2x grid
+            p.y_lo = clip(ky0 - 1, h); p.y_hi = clip(ky1 + 1, h);                    // -> up1 rows [2ky0-2, 2ky1+2)
             SR_DO(run_conv_up2x(n->conv_up1, p, s));
             p.H = 2 * h; p.W = 2 * w; p.src = up1; p.dst_h = up2;
+            p.y_lo = clip(2 * ky0 - 1, 2 * h); p.y_hi = clip(2 * ky1 + 1, 2 * h);    // -> up2 rows [4ky0-2, 4ky1+2)
             SR_DO(run_conv_up2x(n->conv_up2, p, s));
             p.H = 4 * h; p.W = 4 * w;
         }
         p.upsample = 0; p.src = up2; p.dst_h = hr;
+        p.y_lo = clip(4 * ky0 - 1, 4 * h); p.y_hi = clip(4 * ky1 + 1, 4 * h);
         SR_DO(run_conv(n->conv_hr, p, s));
         ConvParams q = c0; q.H = 4 * h; q.W = 4 * w; q.src = hr; q.src_cstride = 64; q.mode = SRM_OUT_NCHW; q.out_nchw = d_out; q.n_valid = 3;
+        q.y_lo = 4 * ky0; q.y_hi = 4 * ky1;
+        q.out_ps = out_plane_stride; q.out_rs = out_row_stride;
+        q.crop_y0 = 4 * ky0; q.crop_y1 = 4 * ky1; q.crop_x0 = 4 * keep_x0; q.crop_x1 = 4 * keep_x1;
         SR_DO(run_conv(n->conv_last, q, s));
     }
 #undef SR_DO
     return K4_OK;
+}
+
+extern "C" int k4_srnet_forward(const k4_srnet* n, const float* d_x, const float* d_cond, int32_t h, int32_t w,
+                                float* d_out, void* d_ws, size_t ws_bytes, k4_stream_t stream) {
+    return k4_srnet_forward_roi(n, d_x, d_cond, h, w, 0, h, 0, w, d_out, (int64_t)16 * h * w, (int64_t)4 * w, d_ws, ws_bytes, stream);
 }

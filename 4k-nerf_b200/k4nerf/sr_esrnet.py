@@ -119,6 +119,39 @@ class SFTNet(nn.Module):
         object.__setattr__(self, '_k4_net', h)
         return h
 
+    def _workspace(self, nbytes, dev, slot=0):
+        pool = self.__dict__.setdefault('_k4_ws_pool', {})
+        ws = pool.get((dev, slot))
+        if ws is None or ws.numel() < nbytes:
+            ws = torch.empty(int(nbytes), device=dev, dtype=torch.uint8)
+            pool[(dev, slot)] = ws
+        return ws
+
+    @torch.no_grad()
+    def forward_roi(self, x, cond, keep, out, ws_slot=0):
+        """The x4 pixels of LR block ``keep = (y0, y1, x0, x1)`` of tile ``x [1,3,h,w]`` / ``cond [1,1,h,w]`` written
+        into ``out``: a ``[3, 4(y1-y0), 4(x1-x0)]`` fp32 CUDA view with unit stride along x (typically a window of the
+        frame).  Same values as ``forward(x, cond)[0, :, 4y0:4y1, 4x0:4x1]``; every layer computes only the rows inside the
+        remaining receptive field of the kept rows (k4_srnet_forward_roi).  Runs on the current stream."""
+        require_cuda(x, cond, out)
+        assert x.dim() == 4 and x.shape[0] == 1 and x.shape[1] == 3 and cond.shape[1] == 1, 'batch 1, 3+1 channels'
+        h, w = int(x.shape[2]), int(x.shape[3])
+        y0, y1, x0, x1 = [int(v) for v in keep]
+        s = self.scale
+        assert out.dtype == torch.float32 and tuple(out.shape) == (3, (y1 - y0) * s, (x1 - x0) * s) and out.stride(2) == 1
+        net = self._get_net()
+        dev = x.device
+        x = x.to(torch.float32).contiguous()
+        cond = cond.to(torch.float32).contiguous()
+        nbytes = int(_lib.lib.k4_srnet_workspace_bytes(net.ptr, h, w))
+        ws = self._workspace(nbytes, dev, ws_slot)
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            _lib.check(_lib.lib.k4_srnet_forward_roi(net.ptr, x.data_ptr(), cond.data_ptr(), h, w, y0, y1, x0, x1,
+                                                     out.data_ptr(), int(out.stride(0)), int(out.stride(1)),
+                                                     ws.data_ptr(), ws.numel(), C.c_void_p(stream)), 'k4_srnet_forward_roi')
+        return out
+
     @torch.no_grad()
     def forward(self, x, cond, fea=None):
         """x [1,3,h,w], cond [1,1,h,w] (CUDA, fp32) -> [1,3,4h,4w]  (lib/sr_esrnet.py:446-465)."""
@@ -127,42 +160,61 @@ class SFTNet(nn.Module):
         require_cuda(x, cond)
         assert x.dim() == 4 and x.shape[0] == 1 and x.shape[1] == 3 and cond.shape[1] == 1, 'batch 1, 3+1 channels'
         h, w = int(x.shape[2]), int(x.shape[3])
-        net = self._get_net()
-        dev = x.device
-        x = x.to(torch.float32).contiguous()
-        cond = cond.to(torch.float32).contiguous()
-        out = torch.empty((1, 3, h * self.scale, w * self.scale), device=dev, dtype=torch.float32)
-        nbytes = int(_lib.lib.k4_srnet_workspace_bytes(net.ptr, h, w))
-        ws = getattr(self, '_k4_ws', None)
-        if ws is None or ws.numel() < nbytes or ws.device != dev:
-            ws = torch.empty(nbytes, device=dev, dtype=torch.uint8)
-            object.__setattr__(self, '_k4_ws', ws)
-        with torch.cuda.device(dev):
-            stream = torch.cuda.current_stream(dev).cuda_stream
-            _lib.check(_lib.lib.k4_srnet_forward(net.ptr, x.data_ptr(), cond.data_ptr(), h, w, out.data_ptr(),
-                                                 ws.data_ptr(), ws.numel(), C.c_void_p(stream)), 'k4_srnet_forward')
+        out = torch.empty((1, 3, h * self.scale, w * self.scale), device=x.device, dtype=torch.float32)
+        self.forward_roi(x, cond, (0, h, 0, w), out[0])
         return out
 
     @torch.no_grad()
-    def tile_process(self, img, cond, tile_size, tile_pad=10, to_cpu=True):
+    def tile_process(self, img, cond, tile_size, tile_pad=10, to_cpu=True, streams=2):
         """SFTNet.tile_process (lib/sr_esrnet.py:467-527): same tile geometry (the 10-pixel pad is far
-        smaller than the receptive field, so the tiling is part of the result); the output is
-        assembled on the device and moved to the CPU once (the reference copies every tile)."""
+        smaller than the receptive field, so the tiling is part of the result).  Every tile's kept block is
+        written by the last convolution straight into the frame (no crop copies), the frame is assembled on
+        the device and moved to the CPU once (the reference copies every tile), and the tiles are dealt to
+        ``streams`` CUDA streams with a workspace each: the tiles are independent, so the launch / fill /
+        drain phases of one tile's ~120 kernels overlap the other tile's work."""
         batch, channel, height, width = img.shape
+        assert batch == 1
         cond = cond.unsqueeze(0)
         s = self.scale
-        output = img.new_zeros((batch, channel, height * s, width * s))
+        dev = img.device
+        output = torch.empty((batch, channel, height * s, width * s), device=dev, dtype=torch.float32)
         tiles_x = math.ceil(width / tile_size)
         tiles_y = math.ceil(height / tile_size)
+        tiles = []
         for y in range(tiles_y):
             for x in range(tiles_x):
                 x0, y0 = x * tile_size, y * tile_size
                 x1, y1 = min(x0 + tile_size, width), min(y0 + tile_size, height)
                 x0p, x1p = max(x0 - tile_pad, 0), min(x1 + tile_pad, width)
                 y0p, y1p = max(y0 - tile_pad, 0), min(y1 + tile_pad, height)
-                out_tile = self(img[:, :, y0p:y1p, x0p:x1p], cond[:, :, y0p:y1p, x0p:x1p])
-                ty, tx = (y0 - y0p) * s, (x0 - x0p) * s
-                output[:, :, y0 * s:y1 * s, x0 * s:x1 * s] = out_tile[:, :, ty:ty + (y1 - y0) * s, tx:tx + (x1 - x0) * s]
+                tiles.append((y0p, y1p, x0p, x1p, y0, y1, x0, x1))
+        n_streams = max(1, min(int(streams), len(tiles)))
+        cur = torch.cuda.current_stream(dev)
+        side = self.__dict__.setdefault('_k4_streams', {})
+        pool = [cur] + [side.setdefault((dev, i), torch.cuda.Stream(dev)) for i in range(1, n_streams)]
+        if n_streams > 1:
+            ready = torch.cuda.Event()
+            ready.record(cur)
+        order = sorted(range(len(tiles)), key=lambda i: -(tiles[i][1] - tiles[i][0]) * (tiles[i][3] - tiles[i][2]))   # big tiles first
+        load = [0] * n_streams
+        for i in order:
+            y0p, y1p, x0p, x1p, y0, y1, x0, x1 = tiles[i]
+            k = min(range(n_streams), key=lambda j: load[j])
+            load[k] += (y1p - y0p) * (x1p - x0p)
+            st = pool[k]
+            with torch.cuda.stream(st):
+                if k > 0:
+                    st.wait_event(ready)
+                xt = img[:, :, y0p:y1p, x0p:x1p].contiguous()
+                ct = cond[:, :, y0p:y1p, x0p:x1p].contiguous()
+                self.forward_roi(xt, ct, (y0 - y0p, y1 - y0p, x0 - x0p, x1 - x0p),
+                                 output[0, :, y0 * s:y1 * s, x0 * s:x1 * s], ws_slot=k)
+                if k > 0:
+                    xt.record_stream(st); ct.record_stream(st)
+        for k in range(1, n_streams):
+            done = torch.cuda.Event()
+            done.record(pool[k])
+            cur.wait_event(done)
         return output.to('cpu') if to_cpu else output
 
     def receptive_halo(self):
@@ -179,7 +231,8 @@ class SFTNet(nn.Module):
         every rank returns the same full frame as single-GPU ``tile_process`` (device resident)."""
         from . import dist as kdist
         return kdist.sr_decode_sharded(lambda x, c: self(x, c), img, cond, tile_size, tile_pad, self.scale,
-                                       self.receptive_halo(), group)
+                                       self.receptive_halo(), group,
+                                       net_roi_fn=lambda x, c, keep, out: self.forward_roi(x, c, keep, out))
 
     def load_network(self, load_path, device, strict=True, param_key='params_ema'):
         """lib/sr_esrnet.py:529-554 (keys may carry a 'module.' prefix; mismatching sizes are skipped

@@ -209,6 +209,17 @@ K4_API size_t k4_srnet_workspace_bytes(const k4_srnet* net, int32_t h, int32_t w
 K4_API int k4_srnet_forward(const k4_srnet* net, const float* d_x, const float* d_cond, int32_t h, int32_t w,
                             float* d_out, void* d_workspace, size_t workspace_bytes, k4_stream_t stream);
 
+/* The same forward when only a block of the tile's output is wanted -- what SFTNet.tile_process does with every tile
+ * (lib/sr_esrnet.py:509-523 crops the 10-pixel pad away and copies the rest into the frame) and what the multi-GPU
+ * decoder does with a tile's row parts.  keep_* select LR rows [keep_y0,keep_y1) x columns [keep_x0,keep_x1) of the
+ * h x w input; their x4 pixels are written straight to d_out[c*out_plane_stride + Y*out_row_stride + X] with (Y, X)
+ * relative to the block's first pixel (pass a pointer into the frame and the frame's strides).  Every layer computes only
+ * the rows inside the remaining receptive field of the kept rows; the values are bit-identical to k4_srnet_forward's. */
+K4_API int k4_srnet_forward_roi(const k4_srnet* net, const float* d_x, const float* d_cond, int32_t h, int32_t w,
+                                int32_t keep_y0, int32_t keep_y1, int32_t keep_x0, int32_t keep_x1,
+                                float* d_out, int64_t out_plane_stride, int64_t out_row_stride,
+                                void* d_workspace, size_t workspace_bytes, k4_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Op-level surface: the 13 functions of the reference extension `render_utils_cuda`
  * (lib/cuda/render_utils.cpp:170-184), bit-identical results, caller-allocated outputs, no host sync.

@@ -196,3 +196,34 @@ def test_large_magnitude_activations_do_not_overflow_fp16(cuda_device):
     rel = (y - ref32).abs().max().item() / ref32.abs().max().item()
     print('large-magnitude decoder: ref range', ref32.abs().max().item(), 'rel maxabs', rel)
     assert rel <= 2e-2, rel
+
+
+def test_forward_roi_block_is_bit_identical_to_the_full_forward(net, cuda_device):
+    """k4_srnet_forward_roi: only the rows inside the remaining receptive field of the kept block are computed by every
+    layer and the last convolution writes the block straight into a strided destination."""
+    g = torch.Generator().manual_seed(41)
+    h, w = 210, 44
+    x = (torch.rand(1, 3, h, w, generator=g) * 1.2 - 0.1).to(cuda_device)
+    c = torch.rand(1, 1, h, w, generator=g).to(cuda_device)
+    full = net(x, c)
+    frame = torch.full((3, 4 * h + 8, 4 * w + 12), -7.0, device=cuda_device)
+    for keep in ((0, h, 0, w), (0, 100, 0, w), (101, 131, 3, 40), (180, h, 10, w), (95, 96, 0, 1)):
+        y0, y1, x0, x1 = keep
+        frame.fill_(-7.0)
+        dst = frame[:, 4:4 + 4 * (y1 - y0), 8:8 + 4 * (x1 - x0)]
+        net.forward_roi(x, c, keep, dst)
+        assert torch.equal(dst, full[0, :, 4 * y0:4 * y1, 4 * x0:4 * x1]), keep
+        frame[:, 4:4 + 4 * (y1 - y0), 8:8 + 4 * (x1 - x0)] = -7.0
+        assert bool((frame == -7.0).all()), ('wrote outside the destination window', keep)
+
+
+def test_tile_process_streams_and_pdl_do_not_change_results(net, cuda_device):
+    g = torch.Generator().manual_seed(42)
+    x = (torch.rand(1, 3, 150, 170, generator=g) * 1.2 - 0.1).to(cuda_device)
+    c = torch.rand(1, 150, 170, generator=g).to(cuda_device)
+    a = net.tile_process(x, c, tile_size=64, tile_pad=10, to_cpu=False, streams=1)
+    b = net.tile_process(x, c, tile_size=64, tile_pad=10, to_cpu=False, streams=2)
+    d = net.tile_process(x, c, tile_size=64, tile_pad=10, to_cpu=False, streams=3)
+    assert torch.equal(a, b) and torch.equal(a, d)
+    ref = sftnet.tile_process(sftnet.random_state_dict(seed=3), x.cpu(), c.cpu(), 64, 10)
+    assert pipeline.psnr(a.cpu(), ref) >= 60.0

@@ -119,7 +119,9 @@ def test_dcvgo_constructor_contract():
     n_inner = int(2 / (2 + 2 * 0.2) * m.world_len / 0.5) + 1
     assert t.numel() == 2 * n_inner and bool((t[1:] > t[:-1]).all())
     assert abs(float(t[0]) - 1.0 / n_inner) < 1e-6 and float(t[-1]) > 100
-    assert m.resolve_mlp_mode('auto') == 'ws' and m.resolve_mlp_mode('tc') == 'ws' and m.resolve_mlp_mode('fp32') == 'fp32'
+    assert m.resolve_mlp_mode('tc') == 'ws' and m.resolve_mlp_mode('fp32') == 'fp32'
+    with pytest.raises(RuntimeError):                 # 'auto' asks the library which kernels cover the DEVICE scene: no CPU path
+        m.resolve_mlp_mode('auto')
     with pytest.raises(NotImplementedError):
         k4nerf.DirectContractedVoxGO(xyz_min=[-1] * 3, xyz_max=[1] * 3, num_voxels=8 ** 3, num_voxels_base=8 ** 3,
                                      alpha_init=1e-2, contracted_norm='l2')

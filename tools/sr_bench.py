@@ -39,8 +39,20 @@ def main():
         return e0.elapsed_time(e1) / iters, out
 
     ms, out = timeit(lambda: net.tile_process(img, cond, 510, to_cpu=False))
-    rec = {'what': 'k4nerf SFTNet.tile_process (tcgen05)', 'hw': [H, W], 'ms_per_frame': ms, 'tflops': flop / ms / 1e9}
+    rec = {'what': 'k4nerf SFTNet.tile_process (tcgen05), tiles on 2 streams', 'hw': [H, W], 'ms_per_frame': ms, 'tflops': flop / ms / 1e9,
+           'pdl': os.environ.get('K4_SR_PDL', '1')}
     print(json.dumps(rec), flush=True)
+    ms1, out1 = timeit(lambda: net.tile_process(img, cond, 510, to_cpu=False, streams=1))
+    print(json.dumps({'what': 'same, tiles one after another on one stream', 'ms_per_frame': ms1, 'tflops': flop / ms1 / 1e9,
+                      'identical_to_2_streams': bool(torch.equal(out, out1))}), flush=True)
+    if '--unit' in sys.argv:           # the decoder unit of one rank of an 8-GPU frame: half a 520x520 tile + halo
+        x = img[:, :, :345, :520].contiguous(); c = cond.unsqueeze(0)[:, :, :345, :520].contiguous()
+        o = torch.empty(3, 255 * 4, 510 * 4, device=dev)
+        msu, _ = timeit(lambda: net.forward_roi(x, c, (0, 255, 0, 510), o))
+        full = torch.empty(3, 345 * 4, 520 * 4, device=dev)
+        msf, _ = timeit(lambda: net.forward_roi(x, c, (0, 345, 0, 520), full))
+        print(json.dumps({'what': '345x520 unit: kept block 255x510 with per-layer row windows vs all rows', 'ms_roi': msu, 'ms_all_rows': msf,
+                          'identical': bool(torch.equal(o, full[:, :1020, :2040]))}), flush=True)
     if no_ref:
         return
     sd_dev = {k: v.to(dev) for k, v in sd.items()}
