@@ -13,6 +13,7 @@
 // The first two are bit-identical to the reference extension (floating-point shape pinned to the
 // reference build's SASS: see the comments at each expression; tests/test_gpu_train_ops.py compares
 // against oracle/_ref).  The last two restate ATen kernels and are held to fp32 rounding.
+#include <cstring>
 #include "k4_march_common.cuh"
 
 namespace {
@@ -185,6 +186,50 @@ __global__ void cumdist_thres_kernel(const float* __restrict__ dist, float thres
         return K4_OK;                                      \
     } while (0)
 
+
+// ---------------------------------------------------------------------------------------------
+// DenseGrid.forward with autograd (lib/grid.py:117-128), the training-side twin of the marcher's
+// in-kernel interpolation: ((xyz - min) / (max - min)).flip(-1) * 2 - 1, ATen grid_sampler_3d
+// (bilinear, zeros padding, align_corners=True) and the [C,M] -> [M,C] transpose in ONE launch
+// instead of the reference's ~6 element-wise kernels + grid_sampler + 2 layout copies; its backward
+// scatters the output gradient into the grid (the reference gets it from ATen's
+// grid_sampler_3d_backward, which also computes the unused gradient w.r.t. the sample positions).
+// One thread per (point, channel); the grid keeps the reference's planar [1,C,X,Y,Z] layout, it is the
+// nn.Parameter the optimiser steps.  Corner order and FMA chain as interp_density (k4_march_common.cuh).
+// ---------------------------------------------------------------------------------------------
+struct GsParams { K4Dev s; const float* grid; const float* xyz; long long M; int C; long long nvox; };
+
+__global__ void grid_sample_fwd_kernel(const __grid_constant__ GsParams p, float* __restrict__ out) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= p.M * p.C) return;
+    const long long m = t / p.C;
+    const int c = (int)(t - m * p.C);
+    const Cell cell = make_cell(p.s, __ldg(p.xyz + 3 * m), __ldg(p.xyz + 3 * m + 1), __ldg(p.xyz + 3 * m + 2));
+    float w[8]; int idx[8];
+    corner_setup(p.s, cell, w, idx);
+    const float* g = p.grid + (long long)c * p.nvox;
+    float acc = __fmul_rn(__ldg(g + idx[0]), w[0]);
+#pragma unroll
+    for (int k = 1; k < 8; ++k) acc = __fmaf_rn(__ldg(g + idx[k]), w[k], acc);
+    out[t] = acc;
+}
+
+__global__ void grid_sample_bwd_kernel(const __grid_constant__ GsParams p, const float* __restrict__ grad_out, float* __restrict__ grad_grid) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= p.M * p.C) return;
+    const float go = __ldg(grad_out + t);
+    if (go == 0.f) return;
+    const long long m = t / p.C;
+    const int c = (int)(t - m * p.C);
+    const Cell cell = make_cell(p.s, __ldg(p.xyz + 3 * m), __ldg(p.xyz + 3 * m + 1), __ldg(p.xyz + 3 * m + 2));
+    float w[8]; int idx[8];
+    corner_setup(p.s, cell, w, idx);
+    float* g = grad_grid + (long long)c * p.nvox;
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+        if (w[k] != 0.f) atomicAdd(g + idx[k], __fmul_rn(w[k], go));       // RED.ADD.F32: no return value, resolved in L2
+}
+
 }  // namespace
 
 extern "C" {
@@ -264,6 +309,44 @@ int k4_op_resample_trilinear(const float* d_src, int32_t C, int32_t X, int32_t Y
     if (!d_src || !d_dst) return K4_ERR_INVALID_ARG;
     const long long n = (long long)X2 * Y2 * Z2;
     resample_trilinear_kernel<<<tr_blocks(n), TR_T, 0, (cudaStream_t)stream>>>(d_src, C, X, Y, Z, d_dst, X2, Y2, Z2);
+    TR_CHECK_LAUNCH();
+}
+
+
+static int gs_params(GsParams& p, const float* d_grid, int32_t C, int32_t X, int32_t Y, int32_t Z, const float* h_xyz_min,
+                     const float* h_xyz_max, const float* d_xyz, int64_t M) {
+    if (!d_grid || !h_xyz_min || !h_xyz_max || C <= 0 || X < 1 || Y < 1 || Z < 1 || M < 0) return K4_ERR_INVALID_ARG;
+    if (M > 0 && !d_xyz) return K4_ERR_INVALID_ARG;
+    if ((long long)X * Y * Z >= (1ll << 31)) return K4_ERR_UNSUPPORTED;
+    memset(&p, 0, sizeof(p));
+    p.s.X = X; p.s.Y = Y; p.s.Z = Z;
+    for (int a = 0; a < 3; ++a) {
+        p.s.xyz_min[a] = h_xyz_min[a]; p.s.xyz_max[a] = h_xyz_max[a];
+        p.s.xyz_len[a] = h_xyz_max[a] - h_xyz_min[a];                        // fp32, as torch: (xyz_max - xyz_min)
+    }
+    p.grid = d_grid; p.xyz = d_xyz; p.M = M; p.C = C; p.nvox = (long long)X * Y * Z;
+    return K4_OK;
+}
+
+int k4_op_grid_sample(const float* d_grid, int32_t C, int32_t X, int32_t Y, int32_t Z, const float* h_xyz_min, const float* h_xyz_max,
+                      const float* d_xyz, int64_t M, float* d_out, k4_stream_t stream) {
+    GsParams p;
+    int st = gs_params(p, d_grid, C, X, Y, Z, h_xyz_min, h_xyz_max, d_xyz, M);
+    if (st != K4_OK) return st;
+    if (M == 0) return K4_OK;
+    if (!d_out) return K4_ERR_INVALID_ARG;
+    grid_sample_fwd_kernel<<<tr_blocks(M * C), TR_T, 0, (cudaStream_t)stream>>>(p, d_out);
+    TR_CHECK_LAUNCH();
+}
+
+int k4_op_grid_sample_backward(const float* d_grad_out, int32_t C, int32_t X, int32_t Y, int32_t Z, const float* h_xyz_min,
+                               const float* h_xyz_max, const float* d_xyz, int64_t M, float* d_grad_grid, k4_stream_t stream) {
+    GsParams p;
+    int st = gs_params(p, d_grad_grid, C, X, Y, Z, h_xyz_min, h_xyz_max, d_xyz, M);
+    if (st != K4_OK) return st;
+    if (M == 0) return K4_OK;
+    if (!d_grad_out) return K4_ERR_INVALID_ARG;
+    grid_sample_bwd_kernel<<<tr_blocks(M * C), TR_T, 0, (cudaStream_t)stream>>>(p, d_grad_out, d_grad_grid);
     TR_CHECK_LAUNCH();
 }
 

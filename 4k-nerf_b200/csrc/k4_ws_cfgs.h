@@ -18,10 +18,10 @@
 
 //        id kind            C   vpe spe W    direct
 #define K4_WS_CFG_LIST(X)                       \
-    X(0,  K4_KIND_DVGO,   12, 0,  0,  128, 1)   \
-    X(1,  K4_KIND_DVGO,   12, 4,  0,  128, 1)   \
     X(2,  K4_KIND_DVGO,   12, 0,  0,  64,  1)   \
+    X(0,  K4_KIND_DVGO,   12, 0,  0,  128, 1)   \
     X(3,  K4_KIND_DVGO,   12, 4,  0,  64,  1)   \
+    X(1,  K4_KIND_DVGO,   12, 4,  0,  128, 1)   \
     X(4,  K4_KIND_DVGO,   15, 4,  0,  128, 0)   \
     X(5,  K4_KIND_DVGO,   16, 6,  0,  128, 1)   \
     X(6,  K4_KIND_DMPIGO, 9,  0,  0,  64,  1)   \

@@ -91,6 +91,10 @@ EXPORTS = {
     'k4_op_maxpool3_thres_and': (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_void_p, C.c_void_p]),
     'k4_op_cumdist_thres': (C.c_int, [C.c_void_p, C.c_float, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
     'k4_op_resample_trilinear': (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
+    'k4_op_grid_sample': (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_float), C.POINTER(C.c_float),
+                                    C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    'k4_op_grid_sample_backward': (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_float), C.POINTER(C.c_float),
+                                             C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     'k4_make_rays_rows': (C.c_int, [C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_int32, C.c_int32, C.c_int32,
                                     C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     'k4_make_rays': (C.c_int, [C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_int32, C.c_int32, C.c_int32,

@@ -9,9 +9,10 @@ import torch.nn as nn
 from . import _lib, grid
 from ._scene import FusedRenderMixin, cached_host, host_float
 from .maintain import GridMaintenanceMixin
+from .coarse import CoarseStageMixin
 
 
-class DirectContractedVoxGO(FusedRenderMixin, GridMaintenanceMixin, nn.Module):
+class DirectContractedVoxGO(FusedRenderMixin, GridMaintenanceMixin, CoarseStageMixin, nn.Module):
     _k4_kind = _lib.K4_KIND_DCVGO
 
     def __init__(self, xyz_min, xyz_max,

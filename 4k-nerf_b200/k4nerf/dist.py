@@ -176,36 +176,98 @@ def render_frame_sharded(render_fn, rays_o, rays_d, viewdirs, H, W, group=None, 
 def sr_units(height, width, tile_size, tile_pad, world_size, halo):
     """Work units of one x4 decode.  The reference's tile geometry (lib/sr_esrnet.py:467-527) is part
     of the result (the 10-pixel pad is far smaller than the receptive field), so the units are the
-    reference tiles; with more ranks than tiles every tile's OUTPUT rows are cut into
-    ``ceil(world/tiles)`` parts, each computed from its rows plus ``halo`` rows above and below,
-    clipped to the PADDED TILE (beyond it the un-split tile sees zero padding too).  With ``halo`` >=
-    the network's receptive radius every part reproduces the un-split tile's pixels exactly.
+    reference tiles; with more ranks than tiles the tiles' OUTPUT rows are cut into row parts, each computed
+    from its rows plus ``halo`` rows above and below, clipped to the PADDED TILE (beyond it the un-split tile
+    sees zero padding too).  With ``halo`` >= the network's receptive radius every part reproduces the
+    un-split tile's pixels exactly.
+
+    Balance: the ranks are dealt to the tiles so that the most expensive part is as cheap as possible (a
+    756-row frame has two 520-row and two 256-row padded tiles: 8 ranks -> 3 + 3 + 1 + 1, not 2 + 2 + 2 + 2),
+    and the cuts inside a tile equalise the parts' cost, where a part costs its kept rows + its pad rows +
+    ~halo/2 rows per cut side (every layer only computes the rows inside the remaining receptive field of the
+    kept rows, SFTNet.forward_roi, so a cut costs half the halo on average).
 
     Returns a list of dicts: ``src`` = (y0, y1, x0, x1) input crop in LR pixels, ``keep`` = (ky, kx)
     offset of the kept block inside the unit's output in LR pixels, ``dst`` = (y0, y1, x0, x1) LR
-    rect of the kept block in the image."""
+    rect of the kept block in the image, ``cost`` = the model above (LR pixels)."""
     import math
     tiles_x = math.ceil(width / tile_size)
     tiles_y = math.ceil(height / tile_size)
-    n_tiles = tiles_x * tiles_y
-    n_split = max(1, math.ceil(world_size / n_tiles))
-    units = []
+    tiles = []
     for ty in range(tiles_y):
         for tx in range(tiles_x):
             x0, y0 = tx * tile_size, ty * tile_size
             x1, y1 = min(x0 + tile_size, width), min(y0 + tile_size, height)
             x0p, x1p = max(x0 - tile_pad, 0), min(x1 + tile_pad, width)
             y0p, y1p = max(y0 - tile_pad, 0), min(y1 + tile_pad, height)
-            rows = y1 - y0
-            for k in range(n_split):
-                ya = y0 + (rows * k) // n_split
-                yb = y0 + (rows * (k + 1)) // n_split
-                if yb <= ya:
-                    continue
-                sa = y0p if k == 0 else max(ya - halo, y0p)
-                sb = y1p if k == n_split - 1 else min(yb + halo, y1p)
-                units.append({'src': (sa, sb, x0p, x1p), 'keep': (ya - sa, x0 - x0p), 'dst': (ya, yb, x0, x1)})
+            tiles.append((y0, y1, x0, x1, y0p, y1p, x0p, x1p))
+    cut_cost = halo / 2.0
+
+    def parts_of(t, n):
+        """Row boundaries of tile t cut into n parts of equal modelled cost; list of (ya, yb, overhead rows)."""
+        y0, y1, _, _, y0p, y1p, _, _ = t
+        rows = y1 - y0
+        n = max(1, min(n, rows))
+        over = [((y0 - y0p) if k == 0 else cut_cost) + ((y1p - y1) if k == n - 1 else cut_cost) for k in range(n)]
+        target = (rows + sum(over)) / n
+        want = [max(1.0, target - o) for o in over]
+        scale = rows / sum(want)
+        edges, acc = [y0], 0.0
+        for k in range(n - 1):
+            acc += want[k] * scale
+            edges.append(min(max(int(round(y0 + acc)), edges[-1] + 1), y1 - (n - 1 - k)))
+        edges.append(y1)
+        return [(edges[k], edges[k + 1], over[k]) for k in range(n)]
+
+    def worst(t, n):
+        w = t[7] - t[6]
+        return max((yb - ya + o) * w for ya, yb, o in parts_of(t, n))
+
+    def split_to(total):
+        sp = [1] * len(tiles)
+        while sum(sp) < total:
+            cand = [i for i in range(len(tiles)) if sp[i] < tiles[i][1] - tiles[i][0]]
+            if not cand:
+                break
+            i = max(cand, key=lambda i: worst(tiles[i], sp[i]))
+            sp[i] += 1
+        return sp
+
+    def max_load(sp):
+        """Largest per-rank cost after longest-first assignment; every unit also pays a fixed ~24 rows of launch /
+        fill / drain overhead (~120 kernels of ~10 us)."""
+        costs = sorted(((yb - ya + o + 24.0) * (t[7] - t[6]) for t, n in zip(tiles, sp) for ya, yb, o in parts_of(t, n)), reverse=True)
+        load = [0.0] * world_size
+        for c in costs:
+            load[load.index(min(load))] += c
+        return max(load)
+
+    # as many units as ranks is the natural choice; a few more can balance better when tiles differ in size
+    # (4 ranks, tiles of 520/520/256/256 rows: 8 units of ~230 rows pack to 483 per rank, 4 whole tiles to 520)
+    splits = min((split_to(total) for total in range(max(world_size, 1), 3 * max(world_size, 1) + 1)),
+                 key=lambda sp: (max_load(sp), sum(sp))) if world_size > 1 else [1] * len(tiles)
+    units = []
+    for t, n in zip(tiles, splits):
+        y0, y1, x0, x1, y0p, y1p, x0p, x1p = t
+        pp = parts_of(t, n)
+        for k, (ya, yb, o) in enumerate(pp):
+            sa = y0p if k == 0 else max(ya - halo, y0p)
+            sb = y1p if k == len(pp) - 1 else min(yb + halo, y1p)
+            units.append({'src': (sa, sb, x0p, x1p), 'keep': (ya - sa, x0 - x0p), 'dst': (ya, yb, x0, x1),
+                          'cost': (yb - ya + o) * (x1p - x0p)})
     return units
+
+
+def sr_assign(units, world_size):
+    """Units of each rank: longest-processing-time first (one unit per rank when there are as many units as ranks)."""
+    order = sorted(range(len(units)), key=lambda i: (-units[i]['cost'], i))
+    load = [0.0] * world_size
+    mine = [[] for _ in range(world_size)]
+    for i in order:
+        r = min(range(world_size), key=lambda r: load[r])
+        load[r] += units[i]['cost']
+        mine[r].append(i)
+    return [sorted(m) for m in mine]
 
 
 def sr_decode_sharded(net_fn, img, cond, tile_size, tile_pad=10, scale=4, halo=80, group=None, net_roi_fn=None):
@@ -222,12 +284,13 @@ def sr_decode_sharded(net_fn, img, cond, tile_size, tile_pad=10, scale=4, halo=8
     s = scale
     units = sr_units(H, W, tile_size, tile_pad, world, halo)
     size = lambda u: C * (u['dst'][1] - u['dst'][0]) * (u['dst'][3] - u['dst'][2]) * s * s
-    per_rank = [sum(size(u) for u in units[r::world]) for r in range(world)]
+    assign = sr_assign(units, world)
+    per_rank = [sum(size(units[i]) for i in assign[r]) for r in range(world)]
     n_pad = max(per_rank) if per_rank else 0
     buf = torch.empty(n_pad, device=img.device, dtype=img.dtype)
     off = 0
     cond4 = cond.unsqueeze(0)
-    for u in units[rank::world]:
+    for u in (units[i] for i in assign[rank]):
         sa, sb, xa, xb = u['src']
         ky, kx = u['keep']
         y0, y1, x0, x1 = u['dst']
@@ -249,7 +312,7 @@ def sr_decode_sharded(net_fn, img, cond, tile_size, tile_pad=10, scale=4, halo=8
     output = torch.empty((1, C, H * s, W * s), device=img.device, dtype=img.dtype)
     for r in range(world):
         off = 0
-        for u in units[r::world]:
+        for u in (units[i] for i in assign[r]):
             y0, y1, x0, x1 = u['dst']
             n = size(u)
             output[0, :, y0 * s:y1 * s, x0 * s:x1 * s] = g[r, off:off + n].view(C, (y1 - y0) * s, (x1 - x0) * s)

@@ -7,9 +7,10 @@ import torch.nn as nn
 from . import _lib, grid
 from ._scene import FusedRenderMixin
 from .maintain import GridMaintenanceMixin
+from .coarse import CoarseStageMixin
 
 
-class DirectMPIGO(FusedRenderMixin, GridMaintenanceMixin, nn.Module):
+class DirectMPIGO(FusedRenderMixin, GridMaintenanceMixin, CoarseStageMixin, nn.Module):
     _k4_kind = _lib.K4_KIND_DMPIGO
 
     def __init__(self, xyz_min, xyz_max,

@@ -7,9 +7,10 @@ import torch.nn as nn
 from . import _lib, grid
 from ._scene import FusedRenderMixin, cached_host, host_float
 from .maintain import GridMaintenanceMixin
+from .coarse import CoarseStageMixin
 
 
-class DirectVoxGO(FusedRenderMixin, GridMaintenanceMixin, nn.Module):
+class DirectVoxGO(FusedRenderMixin, GridMaintenanceMixin, CoarseStageMixin, nn.Module):
     _k4_kind = _lib.K4_KIND_DVGO
 
     def __init__(self, xyz_min, xyz_max,
@@ -155,3 +156,8 @@ def get_rays_of_a_view(H, W, K, c2w, ndc, inverse_y, flip_x, flip_y, mode='cente
                                               out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(),
                                               C.c_void_p(stream)), 'k4_make_rays_rows')
     return out[0], out[1], out[2]
+
+
+# training-ray helpers with the reference's names (lib/dvgo.py:516-544,585-697,761-768), plain torch on top of the above
+from .coarse import (get_rays, get_training_rays, get_training_rays_flatten,          # noqa: E402,F401
+                     get_training_rays_in_maskcache_sampling, batch_indices_generator)

@@ -18,6 +18,43 @@ def create_grid(type, **kwargs):
     raise NotImplementedError(f'k4nerf supports density_type/k0_type "DenseGrid" only, got {type!r}')
 
 
+class _GridSample(torch.autograd.Function):
+    """DenseGrid.forward on the library's fused kernels (csrc/k4_train.cu): forward = normalise + trilinear gather +
+    transpose in one launch, backward = gradient scatter into the grid (the sample positions carry no gradient in the
+    reference either: ray_pts come out of the no-grad samplers)."""
+
+    @staticmethod
+    def forward(ctx, grid, xyz, lo, hi):
+        import ctypes as C
+        from . import _lib
+        from .render_utils_cuda import _p, _s, _call
+        xyz = xyz.detach().reshape(-1, 3).to(torch.float32).contiguous()
+        g = grid.detach().contiguous()
+        Cn, X, Y, Z = (int(v) for v in g.shape[1:])
+        out = torch.empty((xyz.shape[0], Cn), device=g.device, dtype=torch.float32)
+        lo_c, hi_c = (C.c_float * 3)(*lo), (C.c_float * 3)(*hi)
+        with torch.cuda.device(g.device):
+            _call('k4_op_grid_sample', _p(g), Cn, X, Y, Z, lo_c, hi_c, _p(xyz), xyz.shape[0], _p(out), _s(g))
+        ctx.save_for_backward(xyz)
+        ctx.meta = (tuple(grid.shape), lo, hi)
+        del _lib
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        import ctypes as C
+        from .render_utils_cuda import _p, _s, _call
+        (xyz,) = ctx.saved_tensors
+        shape, lo, hi = ctx.meta
+        Cn, X, Y, Z = (int(v) for v in shape[1:])
+        grad_grid = torch.zeros(shape, device=grad_out.device, dtype=torch.float32)
+        go = grad_out.to(torch.float32).contiguous()
+        lo_c, hi_c = (C.c_float * 3)(*lo), (C.c_float * 3)(*hi)
+        with torch.cuda.device(go.device):
+            _call('k4_op_grid_sample_backward', _p(go), Cn, X, Y, Z, lo_c, hi_c, _p(xyz), xyz.shape[0], _p(grad_grid), _s(go))
+        return grad_grid, None, None, None
+
+
 class DenseGrid(nn.Module):
     def __init__(self, channels, world_size, xyz_min, xyz_max, **kwargs):
         super().__init__()
@@ -27,10 +64,26 @@ class DenseGrid(nn.Module):
         self.register_buffer('xyz_max', torch.as_tensor(xyz_max, dtype=torch.float32).clone())
         self.grid = nn.Parameter(torch.zeros([1, channels, *[int(w) for w in world_size]]))
 
+    def _host_box(self):
+        """xyz_min / xyz_max as host floats, cached by the buffers' versions (no per-call device sync)."""
+        key = (self.xyz_min.data_ptr(), self.xyz_min._version, self.xyz_max.data_ptr(), self.xyz_max._version)
+        c = self.__dict__.get('_k4_box')
+        if c is None or c[0] != key:
+            c = (key, tuple(self.xyz_min.detach().cpu().tolist()), tuple(self.xyz_max.detach().cpu().tolist()))
+            self.__dict__['_k4_box'] = c
+        return c[1], c[2]
+
     def forward(self, xyz):
-        """Trilinear lookup with autograd (lib/grid.py:117-128) -- ATen grid_sample; training side only."""
+        """Trilinear lookup with autograd (lib/grid.py:117-128).  CUDA fp32 grids whose sample positions carry no
+        gradient (every caller in the reference) run on the library's fused forward / gradient-scatter kernels
+        (k4_op_grid_sample[_backward]); anything else takes the reference's ATen grid_sample path."""
         import torch.nn.functional as F
         shape = xyz.shape[:-1]
+        if (self.grid.is_cuda and self.grid.dtype == torch.float32 and xyz.is_cuda and not xyz.requires_grad
+                and self.channels > 0 and self.grid.numel() < (1 << 31) * self.channels):
+            lo, hi = self._host_box()
+            out = _GridSample.apply(self.grid, xyz, lo, hi).reshape(*shape, self.channels)
+            return out.squeeze(-1) if self.channels == 1 else out
         xyz = xyz.reshape(1, 1, 1, -1, 3)
         ind_norm = ((xyz - self.xyz_min) / (self.xyz_max - self.xyz_min)).flip((-1,)) * 2 - 1
         out = F.grid_sample(self.grid, ind_norm, mode='bilinear', align_corners=True)

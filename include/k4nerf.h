@@ -295,6 +295,16 @@ K4_API int k4_op_cumdist_thres(const float* d_dist, float thres, int64_t n_rays,
 K4_API int k4_op_resample_trilinear(const float* d_src, int32_t C, int32_t X, int32_t Y, int32_t Z, float* d_dst, int32_t X2,
                                     int32_t Y2, int32_t Z2, k4_stream_t stream);
 
+/* DenseGrid.forward with autograd (lib/grid.py:117-128): trilinear lookup of world points in a planar [1,C,X,Y,Z]
+ * grid -- ((xyz-min)/(max-min)).flip(-1)*2-1, ATen grid_sampler_3d (bilinear, zeros, align_corners=True) and the
+ * [C,M]->[M,C] transpose in one launch -- and its backward: the scatter of the output gradient [M,C] into the grid
+ * gradient [C,X,Y,Z] (ACCUMULATED with atomics: the caller zero-fills), which the reference obtains from ATen's
+ * grid_sampler_3d_backward.  h_xyz_min/max: 3 host floats each.  d_xyz [M,3], d_out / d_grad_out [M,C]. */
+K4_API int k4_op_grid_sample(const float* d_grid, int32_t C, int32_t X, int32_t Y, int32_t Z, const float* h_xyz_min,
+                             const float* h_xyz_max, const float* d_xyz, int64_t M, float* d_out, k4_stream_t stream);
+K4_API int k4_op_grid_sample_backward(const float* d_grad_out, int32_t C, int32_t X, int32_t Y, int32_t Z, const float* h_xyz_min,
+                                      const float* h_xyz_max, const float* d_xyz, int64_t M, float* d_grad_grid, k4_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -60,6 +60,30 @@ def main():
         if world > 1:
             dist.all_reduce(tm, op=dist.ReduceOp.MAX)
         res[regime]['ms_per_frame'] = tm.item()
+        # phase breakdown (max over ranks): the marcher + its all-gather, and the decoder + its all-gather, timed apart
+        x = lr['rgb_marched'].view(H, W, 3).permute(2, 0, 1).unsqueeze(0).contiguous()
+        cond = lr['depth'].view(1, H, W).contiguous()
+        from k4nerf import dvgo as kdvgo
+        frame = list(model.__dict__['_k4_cyclic_frames'].values())[0]
+        kw2 = dict(kw); kw2['render_depth'] = True
+        make = lambda rows: tuple(t.view(-1, 3) for t in kdvgo.get_rays_of_a_view(H, W, K, c2w, False, False, False, False, rows=rows, device=dev))
+        fn = lambda ro, rd, vd, hw, out: model.render_rays(ro, rd, vd, kw2, image_hw=hw, out=out)
+        phases = {'march_gather': lambda: frame.render(make, fn),
+                  'march_only': lambda: (frame.k > 0) and fn(*make(frame.rows), (frame.k, W), frame.out),
+                  'decode_gather': lambda: net.tile_process_sharded(x, cond, tile_size=510)}
+        for name, f in phases.items():
+            f(); torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            e0.record()
+            for _ in range(5):
+                f()
+            e1.record()
+            torch.cuda.synchronize()
+            tp = torch.tensor([e0.elapsed_time(e1) / 5], device=dev)
+            if world > 1:
+                dist.all_reduce(tp, op=dist.ReduceOp.MAX)
+            res[regime][name + '_ms'] = round(tp.item(), 3)
     if rank == 0:
         print(json.dumps({'n_gpus': world, 'frame': '1008x756 -> 4032x3024', **res}), flush=True)
     if world > 1:
