@@ -270,13 +270,14 @@ def sr_assign(units, world_size):
     return [sorted(m) for m in mine]
 
 
-def sr_decode_sharded(net_fn, img, cond, tile_size, tile_pad=10, scale=4, halo=80, group=None, net_roi_fn=None):
+def sr_decode_sharded(net_fn, img, cond, tile_size, tile_pad=10, scale=4, halo=80, group=None, net_units_fn=None):
     """x`scale` decode of ``img [1,C,H,W]`` / ``cond [1,H,W]`` (full frame on every rank) with the units
     of :func:`sr_units` dealt round-robin over the ranks and ONE all-gather of the packed output
     blocks.  ``net_fn(img_crop, cond_crop[1,1,h,w]) -> [1,C,scale*h,scale*w]`` is the decoder
-    (``SFTNet.forward``); ``net_roi_fn(img_crop, cond_crop, (y0,y1,x0,x1), out[C,.,.])`` (``SFTNet.forward_roi``),
-    when given, writes a unit's kept block straight into the packed send buffer and lets every layer skip the
-    rows outside the kept block's remaining receptive field.  Every rank returns the full
+    (``SFTNet.forward``); ``net_units_fn(jobs)`` with ``jobs = [(img_crop, cond_crop, (y0,y1,x0,x1), out[C,.,.]), ...]``
+    (``SFTNet.run_units``), when given, writes every unit's kept block straight into the packed send buffer, lets every
+    layer skip the rows outside the kept block's remaining receptive field and overlaps a rank's units on two
+    streams.  Every rank returns the full
     ``[1,C,scale*H,scale*W]`` frame."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
@@ -290,19 +291,21 @@ def sr_decode_sharded(net_fn, img, cond, tile_size, tile_pad=10, scale=4, halo=8
     buf = torch.empty(n_pad, device=img.device, dtype=img.dtype)
     off = 0
     cond4 = cond.unsqueeze(0)
+    jobs = []
     for u in (units[i] for i in assign[rank]):
         sa, sb, xa, xb = u['src']
         ky, kx = u['keep']
         y0, y1, x0, x1 = u['dst']
         n = size(u)
         blk = buf[off:off + n].view(C, (y1 - y0) * s, (x1 - x0) * s)
-        if net_roi_fn is not None:
-            net_roi_fn(img[:, :, sa:sb, xa:xb].contiguous(), cond4[:, :, sa:sb, xa:xb].contiguous(),
-                       (ky, ky + y1 - y0, kx, kx + x1 - x0), blk)
+        if net_units_fn is not None:
+            jobs.append((img[:, :, sa:sb, xa:xb], cond4[:, :, sa:sb, xa:xb], (ky, ky + y1 - y0, kx, kx + x1 - x0), blk))
         else:
             out = net_fn(img[:, :, sa:sb, xa:xb], cond4[:, :, sa:sb, xa:xb])
             blk.copy_(out[0, :, ky * s:(ky + y1 - y0) * s, kx * s:(kx + x1 - x0) * s])
         off += n
+    if jobs:
+        net_units_fn(jobs)
     if world > 1:
         gathered = torch.empty(world * n_pad, device=img.device, dtype=img.dtype)
         dist.all_gather_into_tensor(gathered, buf, group=group)

@@ -153,6 +153,42 @@ class SFTNet(nn.Module):
         return out
 
     @torch.no_grad()
+    def run_units(self, jobs, streams=2):
+        """``forward_roi`` for a list of independent jobs ``(x_crop, cond_crop, keep, out_view)`` dealt (largest first) to
+        ``streams`` CUDA streams with a workspace each; returns when the current stream has been made to wait for all of
+        them.  Independent units overlap each other's launch / fill / drain phases (~120 kernels per unit)."""
+        if not jobs:
+            return
+        dev = jobs[0][0].device
+        n_streams = max(1, min(int(streams), len(jobs)))
+        cur = torch.cuda.current_stream(dev)
+        side = self.__dict__.setdefault('_k4_streams', {})
+        pool = [cur] + [side.setdefault((dev, i), torch.cuda.Stream(dev)) for i in range(1, n_streams)]
+        if n_streams > 1:
+            ready = torch.cuda.Event()
+            ready.record(cur)
+        order = sorted(range(len(jobs)), key=lambda i: -jobs[i][0].shape[2] * jobs[i][0].shape[3])
+        load = [0] * n_streams
+        used = set()
+        for i in order:
+            x, c, keep, out = jobs[i]
+            k = min(range(n_streams), key=lambda j: load[j])
+            load[k] += x.shape[2] * x.shape[3]
+            st = pool[k]
+            with torch.cuda.stream(st):
+                if k > 0 and k not in used:
+                    st.wait_event(ready)
+                used.add(k)
+                xt, ct = x.contiguous(), c.contiguous()
+                self.forward_roi(xt, ct, keep, out, ws_slot=k)
+                if k > 0:
+                    xt.record_stream(st); ct.record_stream(st)
+        for k in sorted(used - {0}):
+            done = torch.cuda.Event()
+            done.record(pool[k])
+            cur.wait_event(done)
+
+    @torch.no_grad()
     def forward(self, x, cond, fea=None):
         """x [1,3,h,w], cond [1,1,h,w] (CUDA, fp32) -> [1,3,4h,4w]  (lib/sr_esrnet.py:446-465)."""
         if fea is not None:
@@ -188,33 +224,9 @@ class SFTNet(nn.Module):
                 x0p, x1p = max(x0 - tile_pad, 0), min(x1 + tile_pad, width)
                 y0p, y1p = max(y0 - tile_pad, 0), min(y1 + tile_pad, height)
                 tiles.append((y0p, y1p, x0p, x1p, y0, y1, x0, x1))
-        n_streams = max(1, min(int(streams), len(tiles)))
-        cur = torch.cuda.current_stream(dev)
-        side = self.__dict__.setdefault('_k4_streams', {})
-        pool = [cur] + [side.setdefault((dev, i), torch.cuda.Stream(dev)) for i in range(1, n_streams)]
-        if n_streams > 1:
-            ready = torch.cuda.Event()
-            ready.record(cur)
-        order = sorted(range(len(tiles)), key=lambda i: -(tiles[i][1] - tiles[i][0]) * (tiles[i][3] - tiles[i][2]))   # big tiles first
-        load = [0] * n_streams
-        for i in order:
-            y0p, y1p, x0p, x1p, y0, y1, x0, x1 = tiles[i]
-            k = min(range(n_streams), key=lambda j: load[j])
-            load[k] += (y1p - y0p) * (x1p - x0p)
-            st = pool[k]
-            with torch.cuda.stream(st):
-                if k > 0:
-                    st.wait_event(ready)
-                xt = img[:, :, y0p:y1p, x0p:x1p].contiguous()
-                ct = cond[:, :, y0p:y1p, x0p:x1p].contiguous()
-                self.forward_roi(xt, ct, (y0 - y0p, y1 - y0p, x0 - x0p, x1 - x0p),
-                                 output[0, :, y0 * s:y1 * s, x0 * s:x1 * s], ws_slot=k)
-                if k > 0:
-                    xt.record_stream(st); ct.record_stream(st)
-        for k in range(1, n_streams):
-            done = torch.cuda.Event()
-            done.record(pool[k])
-            cur.wait_event(done)
+        jobs = [(img[:, :, y0p:y1p, x0p:x1p], cond[:, :, y0p:y1p, x0p:x1p], (y0 - y0p, y1 - y0p, x0 - x0p, x1 - x0p),
+                 output[0, :, y0 * s:y1 * s, x0 * s:x1 * s]) for (y0p, y1p, x0p, x1p, y0, y1, x0, x1) in tiles]
+        self.run_units(jobs, streams)
         return output.to('cpu') if to_cpu else output
 
     def receptive_halo(self):
@@ -232,7 +244,7 @@ class SFTNet(nn.Module):
         from . import dist as kdist
         return kdist.sr_decode_sharded(lambda x, c: self(x, c), img, cond, tile_size, tile_pad, self.scale,
                                        self.receptive_halo(), group,
-                                       net_roi_fn=lambda x, c, keep, out: self.forward_roi(x, c, keep, out))
+                                       net_units_fn=lambda jobs: self.run_units(jobs, streams=2))
 
     def load_network(self, load_path, device, strict=True, param_key='params_ema'):
         """lib/sr_esrnet.py:529-554 (keys may carry a 'module.' prefix; mismatching sizes are skipped
