@@ -893,15 +893,19 @@ struct SftTcParams {
 };
 
 template <int COUT>
-__global__ void __launch_bounds__(128, (COUT == 64) ? 2 : 4) sft_tc_kernel(const __grid_constant__ SftTcParams p) {
+__global__ void __launch_bounds__(128, 4) sft_tc_kernel(const __grid_constant__ SftTcParams p) {
     extern __shared__ __align__(1024) unsigned char smem[];
     const SftBlob BL = sft_blob_layout(COUT);
     unsigned char* blob = smem;
     unsigned char* atile = smem + ((BL.total + 1023) & ~1023);          // [128][32] fp16 canonical, 8 KB
     uint64_t* mbar = reinterpret_cast<uint64_t*>(atile + 8192);
     uint32_t* tslot = reinterpret_cast<uint32_t*>(atile + 8192 + 16);
-    constexpr int TCOLS = (COUT == 64) ? 256 : 128;
-    constexpr uint32_t D0 = 0, D1S = 64, D1H = 64 + COUT;
+    // Tensor memory: 128 columns for either width, so four CTAs share an SM (the kernel is a chain of dependent phases
+    // with 4 warps per CTA: occupancy is what hides its latencies).  The 64-channel layer runs its second GEMM in two
+    // 32-channel halves: [0,32) packed fp16 hidden layer, [32,64) scale half, [64,96) shift half.
+    constexpr int TCOLS = 128;
+    constexpr int NH = 32;                                  // output channels per second-GEMM pass
+    constexpr uint32_t D0 = 0, D1S = (COUT == 64) ? 32 : 64, D1H = (COUT == 64) ? 64 : 96;
     const int tid = threadIdx.x, warp = tid >> 5;
     for (int i = tid; i < BL.total / 16; i += 128) cp_async16(blob + i * 16, p.blob + i * 16, 16);
     asm volatile("cp.async.commit_group;\n" ::: "memory");
@@ -945,18 +949,6 @@ __global__ void __launch_bounds__(128, (COUT == 64) ? 2 : 4) sft_tc_kernel(const
             __half2 h[4] = {sr_h2sat(a.x, a.y), sr_h2sat(a.z, a.w), sr_h2sat(b.x, b.y), sr_h2sat(b.z, b.w)};
             *reinterpret_cast<uint4*>(atile + tc_canon_off(tid, kc, 4)) = *reinterpret_cast<uint4*>(h);
         }
-        uint4 xraw[COUT / 4];                                   // the x row: COUT fp32 (all of it) or COUT fp16 (first half)
-        if (valid) {
-            if (p.x_f) {
-                const uint4* xp = reinterpret_cast<const uint4*>(p.x_f + pix * 64);
-#pragma unroll
-                for (int q = 0; q < COUT / 4; ++q) xraw[q] = __ldg(xp + q);
-            } else {
-                const uint4* xp = reinterpret_cast<const uint4*>(p.x_h + pix * p.xh_cstride + p.xh_c0);
-#pragma unroll
-                for (int q = 0; q < COUT / 8; ++q) xraw[q] = xp[q];
-            }
-        }
         if (tile + (int)gridDim.x < p.n_tiles) load_cond(tile + gridDim.x);
         asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
@@ -987,35 +979,51 @@ __global__ void __launch_bounds__(128, (COUT == 64) ? 2 : 4) sft_tc_kernel(const
         asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
         __syncthreads();
+#pragma unroll
+        for (int hf = 0; hf < COUT / NH; ++hf) {
+        uint4 xraw[NH / 4];                                     // this half of the x row: NH fp32 (all of it) or NH fp16 (first half);
+        if (valid) {                                            // requested before the GEMM so that it lands behind it
+            if (p.x_f) {
+                const uint4* xp = reinterpret_cast<const uint4*>(p.x_f + pix * 64 + hf * NH);
+#pragma unroll
+                for (int q = 0; q < NH / 4; ++q) xraw[q] = __ldg(xp + q);
+            } else {
+                const uint4* xp = reinterpret_cast<const uint4*>(p.x_h + pix * p.xh_cstride + p.xh_c0 + hf * NH);
+#pragma unroll
+                for (int q = 0; q < NH / 8; ++q) xraw[q] = xp[q];
+            }
+        }
         if (warp == 0 && sr_elect_one()) {
             asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-            const uint32_t idc = sr_idesc(128, COUT);
-            sr_mma_ts(tbase + D1S, tbase + D0 + 0, sr_desc(blob_s + BL.off_b1s, 128, 512), idc, 0);
-            sr_mma_ts(tbase + D1S, tbase + D0 + 8, sr_desc(blob_s + BL.off_b1s + 256, 128, 512), idc, 1);
-            sr_mma_ss(tbase + D1S, sr_desc(blob_s + BL.off_ones, 128, 256), sr_desc(blob_s + BL.off_bias1s, 128, 256), idc, 1);
-            sr_mma_ts(tbase + D1H, tbase + D0 + 16, sr_desc(blob_s + BL.off_b1h, 128, 512), idc, 0);
-            sr_mma_ts(tbase + D1H, tbase + D0 + 24, sr_desc(blob_s + BL.off_b1h + 256, 128, 512), idc, 1);
-            sr_mma_ss(tbase + D1H, sr_desc(blob_s + BL.off_ones, 128, 256), sr_desc(blob_s + BL.off_bias1h, 128, 256), idc, 1);
+            const uint32_t idc = sr_idesc(128, NH);
+            const uint32_t wo = (uint32_t)hf * (NH / 8) * 512, bo = (uint32_t)hf * (NH / 8) * 256;   // row blocks of 8 outputs: 512 B (K=32), 256 B (K=16)
+            sr_mma_ts(tbase + D1S, tbase + D0 + 0, sr_desc(blob_s + BL.off_b1s + wo, 128, 512), idc, 0);
+            sr_mma_ts(tbase + D1S, tbase + D0 + 8, sr_desc(blob_s + BL.off_b1s + wo + 256, 128, 512), idc, 1);
+            sr_mma_ss(tbase + D1S, sr_desc(blob_s + BL.off_ones, 128, 256), sr_desc(blob_s + BL.off_bias1s + bo, 128, 256), idc, 1);
+            sr_mma_ts(tbase + D1H, tbase + D0 + 16, sr_desc(blob_s + BL.off_b1h + wo, 128, 512), idc, 0);
+            sr_mma_ts(tbase + D1H, tbase + D0 + 24, sr_desc(blob_s + BL.off_b1h + wo + 256, 128, 512), idc, 1);
+            sr_mma_ss(tbase + D1H, sr_desc(blob_s + BL.off_ones, 128, 256), sr_desc(blob_s + BL.off_bias1h + bo, 128, 256), idc, 1);
             sr_commit(mbar);
         }
         sr_mbar_wait(mbar, ph); ph ^= 1;
         asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
 #pragma unroll
-        for (int c16 = 0; c16 < COUT / 16; ++c16) {
+        for (int cc = 0; cc < NH / 16; ++cc) {
+            const int c16 = hf * (NH / 16) + cc;
             uint32_t sv[16], hv[16];
-            sr_ld16(tl + D1S + c16 * 16, sv);
-            sr_ld16(tl + D1H + c16 * 16, hv);
+            sr_ld16(tl + D1S + cc * 16, sv);
+            sr_ld16(tl + D1H + cc * 16, hv);
             asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
             if (!valid) continue;
             float x[16];
             if (p.x_f) {
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
-                    const uint4 t = xraw[c16 * 4 + q];
+                    const uint4 t = xraw[cc * 4 + q];
                     x[4 * q] = __uint_as_float(t.x); x[4 * q + 1] = __uint_as_float(t.y); x[4 * q + 2] = __uint_as_float(t.z); x[4 * q + 3] = __uint_as_float(t.w);
                 }
             } else {
-                const uint4 u0 = xraw[c16 * 2], u1 = xraw[c16 * 2 + 1];
+                const uint4 u0 = xraw[cc * 2], u1 = xraw[cc * 2 + 1];
                 const __half2* hp0 = reinterpret_cast<const __half2*>(&u0);
                 const __half2* hp1 = reinterpret_cast<const __half2*>(&u1);
 #pragma unroll
@@ -1040,6 +1048,11 @@ __global__ void __launch_bounds__(128, (COUT == 64) ? 2 : 4) sft_tc_kernel(const
                 d[0] = *reinterpret_cast<uint4*>(&h[0]);
                 d[1] = *reinterpret_cast<uint4*>(&h[4]);
             }
+        }
+        if (hf + 1 < COUT / NH) {          // the next half overwrites D1S / D1H
+            asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+            __syncthreads();
+        }
         }
         asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
         __syncthreads();       // D1S/D1H and the A tile are free again
@@ -1510,7 +1523,7 @@ int launch_sft(const SftParams& p, cudaStream_t s) {
 template <int COUT>
 int launch_sft_tc(const SftTcParams& p, cudaStream_t s) {
     const SftBlob BL = sft_blob_layout(COUT);
-    constexpr int per_sm_c = (COUT == 64) ? 2 : 4;       // TMEM: 256 / 128 columns per CTA
+    constexpr int per_sm_c = 4;                           // TMEM: 128 columns per CTA
     // ask for enough shared memory that no more than `per_sm` CTAs can share an SM: a CTA beyond the
     // TMEM budget would otherwise sit in tcgen05.alloc until a neighbour exits
     int smem = ((BL.total + 1023) & ~1023) + 8192 + 64;

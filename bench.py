@@ -45,6 +45,18 @@ POSES = [(30.0, -30.0), (75.0, -20.0), (140.0, -35.0), (215.0, -25.0), (290.0, -
 HBM_FALLBACK_GBS = 6650.0     # /opt/skills/guides/B200_PROFILING.md fallback
 
 
+_STDOUT_FD = None
+
+
+def emit(text):
+    """Write the result line to the real stdout (see the fd juggling in main for N > 1)."""
+    sys.stdout.flush()
+    if _STDOUT_FD is not None:
+        os.write(_STDOUT_FD, (text + '\n').encode())
+    else:
+        print(text, flush=True)
+
+
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -259,7 +271,13 @@ def main():
     dev = torch.device('cuda', local_rank)
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
-        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')      # keep stdout = the one JSON line
+        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
+        # keep stdout = the one JSON line: NCCL prints its version banner with printf on fd 1, so fd 1 points at stderr
+        # for the whole run and the JSON line goes to the saved descriptor
+        global _STDOUT_FD
+        sys.stdout.flush()
+        _STDOUT_FD = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group('nccl', device_id=dev)
 
     st, model_from_state = build_scene(args.regime)
@@ -430,7 +448,7 @@ def main():
             line['extra'] = extra
         if not args.no_cpu_baseline and world == 1:
             line['cpu_baseline'] = cpu_baseline(st)
-        print(json.dumps(line), flush=True)
+        emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
