@@ -369,8 +369,14 @@ k4_march_ws_kernel(const __grid_constant__ K4Dev s, const __grid_constant__ K4Re
 
             long long ray_i;
             if (rp.image_w > 0) {
-                const int tiles_x = (rp.image_w + 15) >> 4;
-                const int ty = (int)(tile / tiles_x), tx = (int)(tile - (long long)ty * tiles_x);
+                // Tiles are handed out centre first, image border last (rows centre-out, columns centre-out inside a row):
+                // the rays through the middle of the volume are the long ones, so the expensive tiles start early and
+                // the cheap ones fill the tail -- with only 2-3 tiles per warpgroup (a 1008x756 frame on 8 GPUs) the
+                // order of the dynamic queue decides how long the last warpgroup runs.
+                const int tiles_x = (rp.image_w + 15) >> 4, tiles_y = (rp.image_h + 7) >> 3;
+                const int ty_s = (int)(tile / tiles_x), tx_s = (int)(tile - (long long)ty_s * tiles_x);
+                const int ty = (ty_s & 1) ? (tiles_y >> 1) - ((ty_s + 1) >> 1) : (tiles_y >> 1) + (ty_s >> 1);
+                const int tx = (tx_s & 1) ? (tiles_x >> 1) - ((tx_s + 1) >> 1) : (tiles_x >> 1) + (tx_s >> 1);
                 const int px = tx * 16 + (warp_in_wg & 1) * 8 + (lane & 7);
                 const int py = ty * 8 + (warp_in_wg >> 1) * 4 + (lane >> 3);
                 ray_i = (px < rp.image_w && py < rp.image_h) ? (long long)py * rp.image_w + px : -1;

@@ -19,7 +19,7 @@ def main():
     args = [a for a in sys.argv[1:] if not a.startswith('--')]
     no_ref = '--no-ref' in sys.argv
     H, W = (int(args[0]), int(args[1])) if len(args) > 1 else (756, 1008)
-    iters = 3
+    iters = 5
     sd = sftnet.random_state_dict(seed=3, scale=1.0)
     net = k4nerf.SFTNet(3, 4, 64, 5, 32, 1)
     net.load_state_dict(sd)
@@ -45,6 +45,9 @@ def main():
     ms1, out1 = timeit(lambda: net.tile_process(img, cond, 510, to_cpu=False, streams=1))
     print(json.dumps({'what': 'same, tiles one after another on one stream', 'ms_per_frame': ms1, 'tflops': flop / ms1 / 1e9,
                       'identical_to_2_streams': bool(torch.equal(out, out1))}), flush=True)
+    ms4, out4 = timeit(lambda: net.tile_process(img, cond, 510, to_cpu=False, streams=4))
+    print(json.dumps({'what': 'same, all four tiles concurrently (4 streams)', 'ms_per_frame': ms4, 'tflops': flop / ms4 / 1e9,
+                      'identical_to_2_streams': bool(torch.equal(out, out4))}), flush=True)
     if '--unit' in sys.argv:           # the decoder unit of one rank of an 8-GPU frame: half a 520x520 tile + halo
         x = img[:, :, :345, :520].contiguous(); c = cond.unsqueeze(0)[:, :, :345, :520].contiguous()
         o = torch.empty(3, 255 * 4, 510 * 4, device=dev)
