@@ -101,7 +101,11 @@ enum { SRM_STORE_F16 = 0,      // dst_h[c0..c0+N) = act(acc + b)
        SRM_TRUNK = 1,          // dst_f = (acc + b) * scale + add_f                  (conv5: x5*0.2 + x)
        SRM_ADD_STORE_F16 = 2,  // dst_h = fp16((acc + b) + add_f)                    (conv_body + feat)
        SRM_STORE_F32F16 = 3,   // dst_f = acc + b (fp32, 64 ch) and dst_h = fp16     (conv_first: trunk + feat)
-       SRM_OUT_NCHW = 4 };     // out_nchw[c][y][x] = acc + b, c < n_valid          (conv_last)
+       SRM_OUT_NCHW = 4,       // out_nchw[c][y][x] = acc + b, c < n_valid          (conv_last)
+       // conv3x3_ws_kernel only: the SFT layer(s) that follow the convolution run in its epilogue (see epilogue_sft)
+       SRM_STORE_F16_SFT = 5,  // dst_h = fp16(sft(lrelu(acc + b)))                          (conv4 -> sft1)
+       SRM_TRUNK_SFT = 6,      // t = (acc + b) * scale [+ add_f]; dst_f (, dst_f2) = t; dst_h2 = fp16(sft(t))   (conv_first, conv5 of rdb1/2 -> next sft0)
+       SRM_TRUNK_SFT2 = 7 };   // t as above; u = sft(t) * scale2 + add_f2; dst_f = u; dst_h2 = fp16(sft2(u))    (conv5 of rdb3 -> RRDB tail -> next sft0 / sftbody)
 
 struct ConvParams {
     const __half* src; int src_cstride; int src_c0; int cin;       // cin: multiple of 32 (zero padded weights beyond the real Cin)
@@ -125,7 +129,96 @@ struct ConvParams {
     // SRM_OUT_NCHW: output pixel (y, x) of channel c goes to out_nchw[c*out_ps + (y-crop_y0)*out_rs + (x-crop_x0)] when it lies
     // in the crop window [crop_y0,crop_y1) x [crop_x0,crop_x1) (the kept block of a tile, written straight into the frame)
     long long out_ps, out_rs; int crop_y0, crop_y1, crop_x0, crop_x1;
+    // fused SFT epilogues (SRM_*_SFT*): fp16 condition map [P,32], the fragment-ordered operand blocks of the SFT layer(s)
+    // (sft_frag_layout), the fp16 destination of the (last) modulated result, the RRDB input for the block tail
+    const __half* cond16; const unsigned char* sftw; const unsigned char* sftw2; int sft_n;
+    __half* dst_h2; int dst2_cstride, dst2_c0; const float* add_f2; float scale2;
 };
+
+// SFT operands for the in-epilogue mma.sync evaluation: fp16 weights W0 [64][32] (scale_conv0 rows then shift_conv0 rows),
+// W1s [n][32], W1h [n][32] with 40-half row pitch (conflict-free fragment loads), then fp32 biases b0 [64], b1s + 1 [n], b1h [n].
+constexpr int SFTF_PITCH = 40;
+struct SftFrag { int off_w0, off_w1s, off_w1h, off_b0, off_b1s, off_b1h, total; };
+__host__ __device__ inline SftFrag sft_frag_layout(int n) {
+    SftFrag L; int o = 0;
+    L.off_w0 = o; o += 64 * SFTF_PITCH * 2;
+    L.off_w1s = o; o += n * SFTF_PITCH * 2;
+    L.off_w1h = o; o += n * SFTF_PITCH * 2;
+    L.off_b0 = o; o += 64 * 4;
+    L.off_b1s = o; o += n * 4;
+    L.off_b1h = o; o += n * 4;
+    L.total = (o + 15) & ~15;
+    return L;
+}
+constexpr int SFTF_MAX = 2 * (3 * 64 * SFTF_PITCH * 2 + 3 * 64 * 4);      // two 64-channel layers: 32,256 B
+
+__device__ __forceinline__ void sr_hmma(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t sr_pack_sat(float lo, float hi) {
+    uint32_t d;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;\n" : "=r"(d) : "f"(hi), "f"(lo));
+    return d;
+}
+
+// Hidden layer of one SFT layer for 16 pixels: cond fragments `ca` (m16 x k32) x W0 (64 outputs) -> LeakyReLU -> the A
+// fragments of the two second GEMMs (scale branch: hidden 0..31, shift branch: hidden 32..63).  The accumulator fragment
+// of two adjacent n8 blocks IS the A fragment of one k16 step (rows g / g+8, columns 2t..2t+1 / +8).
+__device__ __forceinline__ void sft_hidden(const unsigned char* fw, const SftFrag& L, const uint32_t (&ca)[2][4], int g, int tq,
+                                           uint32_t (&as)[2][4], uint32_t (&ah)[2][4]) {
+    const __half* W0 = reinterpret_cast<const __half*>(fw + L.off_w0);
+    const float* b0 = reinterpret_cast<const float*>(fw + L.off_b0);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        float c[4];
+        c[0] = c[2] = b0[8 * j + 2 * tq]; c[1] = c[3] = b0[8 * j + 2 * tq + 1];
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+            const __half* wr = W0 + (8 * j + g) * SFTF_PITCH + 16 * ks + 2 * tq;
+            sr_hmma(c, ca[ks], *reinterpret_cast<const uint32_t*>(wr), *reinterpret_cast<const uint32_t*>(wr + 8));
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) c[e] = fmaxf(c[e], 0.2f * c[e]);
+        uint32_t (&dst)[2][4] = (j < 4) ? as : ah;
+        const int jj = j & 3;
+        dst[jj >> 1][(jj & 1) * 2 + 0] = sr_pack_sat(c[0], c[1]);          // row g
+        dst[jj >> 1][(jj & 1) * 2 + 1] = sr_pack_sat(c[2], c[3]);          // row g + 8
+    }
+}
+// scale + 1 and shift of output channels 8j .. 8j+7 for the 16 pixels (accumulator fragment layout)
+__device__ __forceinline__ void sft_scale_shift(const unsigned char* fw, const SftFrag& L, const uint32_t (&as)[2][4], const uint32_t (&ah)[2][4],
+                                                int j, int g, int tq, float (&sc)[4], float (&sh)[4]) {
+    const __half* W1s = reinterpret_cast<const __half*>(fw + L.off_w1s);
+    const __half* W1h = reinterpret_cast<const __half*>(fw + L.off_w1h);
+    const float* b1s = reinterpret_cast<const float*>(fw + L.off_b1s);
+    const float* b1h = reinterpret_cast<const float*>(fw + L.off_b1h);
+    sc[0] = sc[2] = b1s[8 * j + 2 * tq]; sc[1] = sc[3] = b1s[8 * j + 2 * tq + 1];
+    sh[0] = sh[2] = b1h[8 * j + 2 * tq]; sh[1] = sh[3] = b1h[8 * j + 2 * tq + 1];
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks) {
+        const __half* ws = W1s + (8 * j + g) * SFTF_PITCH + 16 * ks + 2 * tq;
+        const __half* wh = W1h + (8 * j + g) * SFTF_PITCH + 16 * ks + 2 * tq;
+        sr_hmma(sc, as[ks], *reinterpret_cast<const uint32_t*>(ws), *reinterpret_cast<const uint32_t*>(ws + 8));
+        sr_hmma(sh, ah[ks], *reinterpret_cast<const uint32_t*>(wh), *reinterpret_cast<const uint32_t*>(wh + 8));
+    }
+}
+// 16 lanes x 8*NB columns of an fp32 accumulator in the mma.sync m16n8 accumulator-fragment layout: registers 4j..4j+3 of a
+// thread = (row g, cols 8j+2t, +1), (row g+8, same cols) -- tools/micro/tmem_ld_shapes.cu checks this on the device
+template <int NB> __device__ __forceinline__ void sr_ld_frag(uint32_t taddr, uint32_t (&v)[4 * NB]);
+template <> __device__ __forceinline__ void sr_ld_frag<4>(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile("tcgen05.ld.sync.aligned.16x256b.x4.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]) : "r"(taddr));
+}
+template <> __device__ __forceinline__ void sr_ld_frag<8>(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile("tcgen05.ld.sync.aligned.16x256b.x8.b32 "
+                 "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];\n"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                   "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                   "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31]) : "r"(taddr));
+}
 
 // Programmatic dependent launch: every decoder kernel is launched with programmaticStreamSerialization, so its CTAs are
 // scheduled while the previous kernel drains; the set-up above this point (barrier init, TMEM allocation, constant
@@ -335,6 +428,140 @@ __device__ __forceinline__ void ws_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" :: "r"(sr_s32(bar)) : "memory");
 }
 
+// ---------------------------------------------------------------------------------------------
+// Epilogue with the following SFT layer(s) folded in (SRM_*_SFT* modes).  The 36 SFT layers of the decoder are 0.2 % of
+// its FLOPs but were 26 % of a tile's time as separate passes over the activations (profiles/r2_summary.md); here they
+// cost no memory pass at all.  Per 16 pixels a warp evaluates the layer's two small MLPs with mma.sync (HMMA) straight
+// from registers -- cond row fragments (fp16, [P,32]) x W0 -> LeakyReLU -> re-used as A fragments -> W1s / W1h -- and reads the
+// convolution's accumulator from tensor memory in the SAME fragment layout (tcgen05.ld.16x256b), so scale, shift and the
+// value they modulate meet in registers with no shuffle.  No tensor-memory scratch, no handshake with the MMA warp.
+// Rows of a thread: pixels g and g+8 of the 16 (two image rows of the 16x8-pixel M tile), channels 8j+2t, +1 per block j.
+// ---------------------------------------------------------------------------------------------
+template <int N>
+__device__ __forceinline__ void epilogue_sft(const ConvParams& p, const unsigned char* fw, const float* sbias, uint32_t tacc0,
+                                             int m_lo, int m_hi, int y0, int x0, int q, int lane) {
+    constexpr int NB = N / 8;
+    constexpr int NACC = N;
+    const int g = lane >> 2, tq = lane & 3;
+    const SftFrag L1 = sft_frag_layout(p.sft_n);
+    const SftFrag L2 = sft_frag_layout(64);
+    const unsigned char* fw2 = fw + L1.total;
+    const bool two = (N == 64) && p.mode == SRM_TRUNK_SFT2;
+    const bool trunk = p.mode != SRM_STORE_F16_SFT;
+    const int nblk = 2 * (m_hi - m_lo);                          // 16-pixel blocks of this warp: (M tile, half)
+    // Every global load of a block is issued before the block's arithmetic (the cond fragments of block b+1 even before
+    // block b's): the epilogue is a chain of dependent steps on 8 warps, a load issued where it is used costs its full
+    // latency (the first version of this function spent 2/3 of its time there).
+    auto coords = [&](int blk, size_t& pixA, bool& inA, bool& inB) {
+        const int m = m_lo + (blk >> 1), h = blk & 1;
+        const int rA = 32 * q + 16 * h + g;                       // row of the M tile: pixel (rA >> 3, rA & 7); the second is rA + 8
+        const int pyA = y0 + (rA >> 3), px = x0 + m * 8 + (rA & 7);
+        inA = (pyA < p.y_hi) & (px < p.W); inB = (pyA + 1 < p.y_hi) & (px < p.W);
+        pixA = (size_t)pyA * p.W + px;
+    };
+    auto load_cond = [&](int blk, uint32_t (&c)[2][4]) {
+        size_t pixA; bool inA, inB;
+        coords(blk, pixA, inA, inB);
+        const __half* cA = p.cond16 + (inA ? pixA : 0) * 32 + 2 * tq;
+        const __half* cB = p.cond16 + (inB ? pixA + p.W : 0) * 32 + 2 * tq;
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+            c[ks][0] = __ldg(reinterpret_cast<const unsigned int*>(cA + 16 * ks));
+            c[ks][1] = __ldg(reinterpret_cast<const unsigned int*>(cB + 16 * ks));
+            c[ks][2] = __ldg(reinterpret_cast<const unsigned int*>(cA + 16 * ks + 8));
+            c[ks][3] = __ldg(reinterpret_cast<const unsigned int*>(cB + 16 * ks + 8));
+        }
+    };
+    uint32_t cn[2][4];
+    load_cond(0, cn);
+#pragma unroll 1
+    for (int blk = 0; blk < nblk; ++blk) {
+        size_t pixA; bool inA, inB;
+        coords(blk, pixA, inA, inB);
+        const size_t pixB = pixA + p.W;
+        uint32_t ca[2][4];
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) ca[ks][e] = cn[ks][e];
+        if (blk + 1 < nblk) load_cond(blk + 1, cn);
+        // residual rows (fp32 trunk, and the RRDB input for the block tail) travel through a rolling window of PF channel
+        // blocks: block j+PF is requested when block j is consumed -- enough bytes in flight to cover the memory latency
+        // without holding the whole 256-byte rows in registers (which spills: 168 registers per thread is the limit here)
+        constexpr int PF = (NB < 4) ? NB : 4;
+        float2 rA[PF], rB[PF], xA[PF], xB[PF];
+        auto load_res = [&](int j, int slot) {
+            rA[slot] = rB[slot] = make_float2(0.f, 0.f);
+            if (p.add_f) {
+                if (inA) rA[slot] = __ldg(reinterpret_cast<const float2*>(p.add_f + pixA * 64 + 8 * j + 2 * tq));
+                if (inB) rB[slot] = __ldg(reinterpret_cast<const float2*>(p.add_f + pixB * 64 + 8 * j + 2 * tq));
+            }
+            if (two) {
+                xA[slot] = xB[slot] = make_float2(0.f, 0.f);
+                if (inA) xA[slot] = __ldg(reinterpret_cast<const float2*>(p.add_f2 + pixA * 64 + 8 * j + 2 * tq));
+                if (inB) xB[slot] = __ldg(reinterpret_cast<const float2*>(p.add_f2 + pixB * 64 + 8 * j + 2 * tq));
+            }
+        };
+        if (trunk) {
+#pragma unroll
+            for (int j = 0; j < PF; ++j) load_res(j, j);
+        }
+        const uint32_t tblk = tacc0 + (uint32_t)((m_lo + (blk >> 1)) * NACC) + ((uint32_t)(16 * (blk & 1)) << 16);
+        uint32_t as[2][4], ah[2][4], as2[2][4], ah2[2][4];
+        sft_hidden(fw, L1, ca, g, tq, as, ah);
+        if (two) sft_hidden(fw2, L2, ca, g, tq, as2, ah2);
+#pragma unroll 1
+        for (int jg = 0; jg < NB; jg += PF)
+#pragma unroll
+        for (int jj = 0; jj < PF; ++jj) {
+            const int j = jg + jj;
+            uint32_t acc[4];
+            asm volatile("tcgen05.ld.sync.aligned.16x256b.x1.b32 {%0,%1,%2,%3}, [%4];\n"
+                         : "=r"(acc[0]), "=r"(acc[1]), "=r"(acc[2]), "=r"(acc[3]) : "r"(tblk + 8 * j));
+            float sc[4], sh[4];
+            sft_scale_shift(fw, L1, as, ah, j, g, tq, sc, sh);
+            asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+            const int ch = 8 * j + 2 * tq;
+            float v[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) v[e] = __uint_as_float(acc[e]) + sbias[ch + (e & 1)];
+            if (!trunk) {                       // SRM_STORE_F16_SFT
+#pragma unroll
+                for (int e = 0; e < 4; ++e) { const float a = p.lrelu > 0.f ? fmaxf(v[e], p.lrelu * v[e]) : v[e]; v[e] = fmaf(a, sc[e], sh[e]); }
+                if (inA) *reinterpret_cast<uint32_t*>(p.dst_h + pixA * p.dst_cstride + p.dst_c0 + ch) = sr_pack_sat(v[0], v[1]);
+                if (inB) *reinterpret_cast<uint32_t*>(p.dst_h + pixB * p.dst_cstride + p.dst_c0 + ch) = sr_pack_sat(v[2], v[3]);
+                continue;
+            }
+            const int sl = jj;
+            float t[4] = {fmaf(v[0], p.scale, rA[sl].x), fmaf(v[1], p.scale, rA[sl].y), fmaf(v[2], p.scale, rB[sl].x), fmaf(v[3], p.scale, rB[sl].y)};
+            const float2 xa = xA[sl], xb = xB[sl];
+            if (j + PF < NB) load_res(j + PF, sl);
+            if (!two) {                         // SRM_TRUNK_SFT
+                if (inA) {
+                    *reinterpret_cast<float2*>(p.dst_f + pixA * 64 + ch) = make_float2(t[0], t[1]);
+                    if (p.dst_f2) *reinterpret_cast<float2*>(p.dst_f2 + pixA * 64 + ch) = make_float2(t[0], t[1]);
+                }
+                if (inB) {
+                    *reinterpret_cast<float2*>(p.dst_f + pixB * 64 + ch) = make_float2(t[2], t[3]);
+                    if (p.dst_f2) *reinterpret_cast<float2*>(p.dst_f2 + pixB * 64 + ch) = make_float2(t[2], t[3]);
+                }
+#pragma unroll
+                for (int e = 0; e < 4; ++e) t[e] = fmaf(t[e], sc[e], sh[e]);
+            } else {                            // SRM_TRUNK_SFT2: u = sft(t) * scale2 + x_in -> trunk; then the next layer on u
+                t[0] = fmaf(fmaf(t[0], sc[0], sh[0]), p.scale2, xa.x); t[1] = fmaf(fmaf(t[1], sc[1], sh[1]), p.scale2, xa.y);
+                t[2] = fmaf(fmaf(t[2], sc[2], sh[2]), p.scale2, xb.x); t[3] = fmaf(fmaf(t[3], sc[3], sh[3]), p.scale2, xb.y);
+                if (inA) *reinterpret_cast<float2*>(p.dst_f + pixA * 64 + ch) = make_float2(t[0], t[1]);
+                if (inB) *reinterpret_cast<float2*>(p.dst_f + pixB * 64 + ch) = make_float2(t[2], t[3]);
+                sft_scale_shift(fw2, L2, as2, ah2, j, g, tq, sc, sh);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) t[e] = fmaf(t[e], sc[e], sh[e]);
+            }
+            if (inA) *reinterpret_cast<uint32_t*>(p.dst_h2 + pixA * p.dst2_cstride + p.dst2_c0 + ch) = sr_pack_sat(t[0], t[1]);
+            if (inB) *reinterpret_cast<uint32_t*>(p.dst_h2 + pixB * p.dst2_cstride + p.dst2_c0 + ch) = sr_pack_sat(t[2], t[3]);
+        }
+    }
+}
+
 template <int N>
 __global__ void __launch_bounds__(WS_THREADS, 1) conv3x3_ws_kernel(const __grid_constant__ ConvParams p, const __grid_constant__ CUtensorMap tmap) {
     using C = WsCfg<N>;
@@ -345,9 +572,18 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv3x3_ws_kernel(const __grid_
     uint64_t* acc_empty = acc_full + 2;                                          // [2]   count 128 (epilogue)
     uint32_t* tslot = reinterpret_cast<uint32_t*>(acc_empty + 2);
     float* sbias = reinterpret_cast<float*>(smem + C::NST * C::STAGE + 256);    // [64]
+    unsigned char* sftw_s = smem + C::NST * C::STAGE + 512;                      // SFT operand block(s) of the fused epilogue modes
     const int tid = threadIdx.x, warp = tid >> 5;
     const int n_epi = p.use_tma ? 256 : 128;                                     // epilogue threads (8 or 4 warps)
     if (tid < 64) sbias[tid] = p.bias[tid];
+    if (p.mode >= SRM_STORE_F16_SFT) {                                           // constants: may be staged before the PDL wait
+        const int n1 = sft_frag_layout(p.sft_n).total;
+        for (int i = tid; i < n1 / 16; i += WS_THREADS) reinterpret_cast<uint4*>(sftw_s)[i] = __ldg(reinterpret_cast<const uint4*>(p.sftw) + i);
+        if (p.mode == SRM_TRUNK_SFT2) {
+            const int n2 = sft_frag_layout(64).total;
+            for (int i = tid; i < n2 / 16; i += WS_THREADS) reinterpret_cast<uint4*>(sftw_s + n1)[i] = __ldg(reinterpret_cast<const uint4*>(p.sftw2) + i);
+        }
+    }
     const int tiles_x = (p.W + WS_TX - 1) / WS_TX, tiles_y = (p.y_hi - p.y_lo + SR_TY - 1) / SR_TY;
     const int n_tiles = tiles_x * tiles_y;
     const int nchunks = p.cin / SR_CK;
@@ -497,6 +733,14 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv3x3_ws_kernel(const __grid_
             const unsigned a = it & 1;
             sr_mbar_wait(acc_full + a, (it >> 1) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+            if (p.mode >= SRM_STORE_F16_SFT) {
+                if (N >= 32) {
+                    epilogue_sft<(N >= 32) ? N : 32>(p, sftw_s, sbias, tl + a * WS_TM * C::NACC, m_lo, m_hi, y0, x0, warp & 3, tid & 31);
+                }
+                asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+                ws_arrive(acc_empty + a);
+                continue;
+            }
 #pragma unroll 1
             for (int m = m_lo; m < m_hi; ++m) {
                 const int py = y0 + (et >> 3), px = x0 + m * 8 + (et & 7);
@@ -1083,8 +1327,27 @@ __global__ void pack_sft_blob_kernel(const float* __restrict__ w, unsigned char*
     if (i < 128) { put(BL.off_ones, i, 0, 2, 1.f); put(BL.off_ones, i, 1, 2, 1.f); }
 }
 
+// fp32 SFT weights (sft_kernel packing order) -> fragment-ordered block of the fused epilogues (sft_frag_layout)
+__global__ void pack_sft_frag_kernel(const float* __restrict__ w, unsigned char* __restrict__ dst, int cout) {
+    const SftFrag L = sft_frag_layout(cout);
+    const float* s0 = w; const float* s0b = s0 + 1024; const float* h0 = s0b + 32; const float* h0b = h0 + 1024;
+    const float* s1 = h0b + 32; const float* s1b = s1 + cout * 32; const float* h1 = s1b + cout; const float* h1b = h1 + cout * 32;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < 64 * 32) {
+        const int n = i >> 5, k = i & 31;
+        reinterpret_cast<__half*>(dst + L.off_w0)[n * SFTF_PITCH + k] = __float2half_rn(n < 32 ? s0[n * 32 + k] : h0[(n - 32) * 32 + k]);
+    }
+    if (i < cout * 32) {
+        const int n = i >> 5, k = i & 31;
+        reinterpret_cast<__half*>(dst + L.off_w1s)[n * SFTF_PITCH + k] = __float2half_rn(s1[n * 32 + k]);
+        reinterpret_cast<__half*>(dst + L.off_w1h)[n * SFTF_PITCH + k] = __float2half_rn(h1[n * 32 + k]);
+    }
+    if (i < 64) reinterpret_cast<float*>(dst + L.off_b0)[i] = i < 32 ? s0b[i] : h0b[i - 32];
+    if (i < cout) { reinterpret_cast<float*>(dst + L.off_b1s)[i] = s1b[i] + 1.f; reinterpret_cast<float*>(dst + L.off_b1h)[i] = h1b[i]; }
+}
+
 // CondNet: conv3x3(1->64) lrelu, 1x1 64->64 lrelu, 1x1 64->64 lrelu, 1x1 64->32   (lib/sr_esrnet.py:440-444)
-struct CondParams { const float* cond_in; const float* w; float* cond_out; int H, W; int y_lo, y_hi; };   // w: c0 [64][9], b0[64], c2 [64][64], b2, c4 [64][64], b4, c6 [32][64], b6
+struct CondParams { const float* cond_in; const float* w; float* cond_out; int H, W; int y_lo, y_hi; __half* cond16; };   // w: c0 [64][9], b0[64], c2 [64][64], b2, c4 [64][64], b4, c6 [32][64], b6
 
 __global__ void __launch_bounds__(128) condnet_kernel(const __grid_constant__ CondParams p) {
     constexpr int NW = 64 * 9 + 64 + 2 * (64 * 64 + 64) + 32 * 64 + 32;
@@ -1133,6 +1396,7 @@ __global__ void __launch_bounds__(128) condnet_kernel(const __grid_constant__ Co
 #pragma unroll
         for (int k = 0; k < 64; ++k) v = fmaf(c6[o * 64 + k], a[k], v);
         p.cond_out[pix * 32 + o] = v;
+        if (p.cond16) p.cond16[pix * 32 + o] = __float2half_rn(v);         // operand of the fused SFT epilogues
     }
 }
 
@@ -1222,7 +1486,7 @@ __global__ void pack_conv_k64_kernel(const float* __restrict__ W, __half* __rest
 // ------------------------------------------------------------------------------------------------
 struct SrConv { unsigned char* wpack; float* bias; int cin_pad, cout, npad; unsigned char* wphase[4];
                 __half* wk64; __half* wk64_phase[4]; };       // conv3x3_k64_kernel packs (Cin == 64 layers only)
-struct SrSft { float* w; unsigned char* blob; int cout; };
+struct SrSft { float* w; unsigned char* blob; unsigned char* frag; int cout; };
 
 struct k4_srnet {
     int num_feat, num_block, num_grow, num_cond, n_in, scale;
@@ -1318,6 +1582,12 @@ int make_sft(k4_srnet* n, SrSft& f, const float* const* pw, int cout, cudaStream
     K4_CUDA_TRY(cudaMemsetAsync(f.blob, 0, BL.total, s));
     pack_sft_blob_kernel<<<8, 256, 0, s>>>(f.w, f.blob, cout);
     K4_CUDA_TRY(cudaGetLastError());
+    const SftFrag FL = sft_frag_layout(cout);
+    st = sr_alloc(n, (void**)&f.frag, (size_t)FL.total);
+    if (st) return st;
+    K4_CUDA_TRY(cudaMemsetAsync(f.frag, 0, FL.total, s));
+    pack_sft_frag_kernel<<<8, 256, 0, s>>>(f.w, f.frag, cout);
+    K4_CUDA_TRY(cudaGetLastError());
     return K4_OK;
 }
 
@@ -1412,14 +1682,19 @@ static bool sr_no_tma() {
 template <int N>
 int launch_conv_ws(ConvParams p, cudaStream_t s) {
     using C = WsCfg<N>;
-    if (int st = sr_set_smem(conv3x3_ws_kernel<N>, 3 + sr_bit_n(N), C::SMEM)) return st;
+    if (int st = sr_set_smem(conv3x3_ws_kernel<N>, 3 + sr_bit_n(N), C::SMEM + SFTF_MAX)) return st;
     const int sms = sr_dev()->sms;
     alignas(64) CUtensorMap tm;
     memset(&tm, 0, sizeof(tm));
     p.use_tma = (!p.upsample && !sr_no_tma() && sr_make_tmap(p, &tm)) ? 1 : 0;
     const int tiles = ((p.W + WS_TX - 1) / WS_TX) * ((p.y_hi - p.y_lo + SR_TY - 1) / SR_TY);
     if (tiles <= 0) return K4_OK;
-    K4_CUDA_TRY(sr_launch(conv3x3_ws_kernel<N>, (unsigned)(tiles < sms ? tiles : sms), WS_THREADS, C::SMEM, s, p, tm));
+    size_t smem = C::SMEM;
+    if (p.mode >= SRM_STORE_F16_SFT) {
+        if (!p.use_tma || N < 32 || !p.cond16 || !p.sftw) return K4_ERR_UNSUPPORTED;     // fused epilogues: TMA mode (8 epilogue warps) only
+        smem += sft_frag_layout(p.sft_n).total + (p.mode == SRM_TRUNK_SFT2 ? sft_frag_layout(64).total : 0);
+    }
+    K4_CUDA_TRY(sr_launch(conv3x3_ws_kernel<N>, (unsigned)(tiles < sms ? tiles : sms), WS_THREADS, smem, s, p, tm));
     return K4_OK;
 }
 
@@ -1610,13 +1885,14 @@ extern "C" int k4_srnet_create(const k4_srnet_desc* d, k4_stream_t stream, k4_sr
 }
 
 // workspace layout for an h x w tile (P = h*w LR pixels)
-struct SrWs { size_t in16, cond32, feat, trunkA, trunkB, cat, sbody, bf, up1, up2, hr, total; };
+struct SrWs { size_t in16, cond32, cond16, feat, trunkA, trunkB, cat, cat2, sbody, bf, up1, up2, hr, total; };
 static SrWs sr_ws(int h, int w) {
     const size_t P = (size_t)h * w;
     SrWs o; size_t off = 0;
     auto take = [&](size_t b) { size_t r = off; off += (b + 255) & ~(size_t)255; return r; };
     o.in16 = take(P * 32 * 2); o.cond32 = take(P * 32 * 4); o.feat = take(P * 64 * 4);
     o.trunkA = take(P * 64 * 4); o.trunkB = take(P * 64 * 4); o.cat = take(P * 192 * 2);
+    o.cat2 = take(P * 192 * 2); o.cond16 = take(P * 32 * 2);         // fused SFT epilogues: dense blocks alternate between two concat buffers
     o.sbody = take(P * 64 * 2); o.bf = take(P * 64 * 2);
     o.up1 = take(P * 4 * 64 * 2); o.up2 = take(P * 16 * 64 * 2); o.hr = take(P * 16 * 64 * 2);
     o.total = off;
@@ -1650,6 +1926,10 @@ extern "C" int k4_srnet_forward_roi(const k4_srnet* n, const float* d_x, const f
     float* tA = (float*)(ws + L.trunkA); float* tB = (float*)(ws + L.trunkB); __half* cat = (__half*)(ws + L.cat);
     __half* sbody = (__half*)(ws + L.sbody); __half* bf = (__half*)(ws + L.bf);
     __half* up1 = (__half*)(ws + L.up1); __half* up2 = (__half*)(ws + L.up2); __half* hr = (__half*)(ws + L.hr);
+    __half* cat2 = (__half*)(ws + L.cat2); __half* cond16 = (__half*)(ws + L.cond16);
+    // K4_SR_FUSE_SFT=0: every SFT layer as its own sft_tc_kernel pass (the round-1 structure, kept as the A/B reference)
+    const char* fenv = getenv("K4_SR_FUSE_SFT");                   // read per call: tests compare both structures in one process
+    const bool fuse = !(fenv && fenv[0] == '0') && !sr_use_v1() && !sr_no_tma();
     const int ky0 = keep_y0, ky1 = keep_y1;
     // Remaining receptive radius (LR rows) behind each layer, from the output backwards: conv_last / conv_hr / up2 / up1
     // need 1/4 + 1/4 + 1/4 + 1/2 LR rows (handled exactly in high-resolution rows below), conv_body 1, every 3x3 conv of a
@@ -1661,7 +1941,7 @@ extern "C" int k4_srnet_forward_roi(const k4_srnet* n, const float* d_x, const f
     K4_CUDA_TRY(sr_launch(nchw_to_nhwc32_kernel, (unsigned)((P * 32 + 255) / 256), 256, 0, s, d_x, in16, 3, P));
     {
         const SrRows rr = sr_rows(ky0, ky1, 3 + 5 * nrdb + 5, h);          // every SFT layer inside the window reads it
-        CondParams cp{d_cond, n->condnet_w, cond32, h, w, rr.lo, rr.hi};
+        CondParams cp{d_cond, n->condnet_w, cond32, h, w, rr.lo, rr.hi, fuse ? cond16 : nullptr};
         constexpr int NW = 64 * 9 + 64 + 2 * (64 * 64 + 64) + 32 * 64 + 32;
         SR_DO(sr_set_smem(condnet_kernel, 11, NW * 4));
         const long long np = (long long)(rr.hi - rr.lo) * w;
@@ -1671,55 +1951,108 @@ extern "C" int k4_srnet_forward_roi(const k4_srnet* n, const float* d_x, const f
     c0.H = h; c0.W = w;
     auto rows = [&](ConvParams& p, int r) { const SrRows q = sr_rows(ky0, ky1, r, h); p.y_lo = q.lo; p.y_hi = q.hi; };
     auto win = [&](SftParams& sp, int r) { const SrRows q = sr_rows(ky0, ky1, r, h); sp.p0 = (long long)q.lo * w; sp.P = (long long)(q.hi - q.lo) * w; };
-    {   // feat = conv_first(x): fp32 into `feat` and into trunk A (the initial trunk)
-        ConvParams p = c0; p.src = in16; p.src_cstride = 32; p.src_c0 = 0; p.mode = SRM_STORE_F32F16; p.dst_f = feat; p.dst_f2 = tA;
-        rows(p, 3 + 5 * nrdb);
-        SR_DO(run_conv(n->conv_first, p, s));
-    }
-    for (int i = 0; i < n->num_block; ++i) {
-        // RRDB_SFT.forward: trunk A holds x (kept for the block's tail), RDBs update A -> B -> B -> B
-        const float* cur = tA;
-        for (int j = 0; j < 3; ++j) {
-            const int k = nrdb - 1 - (3 * i + j);                              // dense blocks still to come
-            const int base = 3 + 5 * k;                                        // rows(base): this block's output
-            {   // xc0 = sft0(x) -> cat[0:64]
-                SftParams sp{}; sp.cond = cond32; sp.x_f = cur; sp.dst_h = cat; sp.dst_cstride = 192; sp.dst_c0 = 0;
-                win(sp, base + 5);
-                SR_DO(run_sft(n->rdb_sft[i][j][0], sp, s));
-            }
-            for (int c = 0; c < 4; ++c) {   // x{c+1} = lrelu(conv(cat[0:64+32c])) -> cat[64+32c : 96+32c]
-                ConvParams p = c0; p.src = cat; p.src_cstride = 192; p.src_c0 = 0; p.mode = SRM_STORE_F16; p.lrelu = 0.2f;
-                p.dst_h = cat; p.dst_cstride = 192; p.dst_c0 = 64 + 32 * c;
-                rows(p, base + 4 - c);
-                SR_DO(run_conv(n->rdb_conv[i][j][c], p, s));
-            }
-            {   // xc1 = sft1(x4) in place: cat[160:192]
-                SftParams sp{}; sp.cond = cond32; sp.x_h = cat; sp.xh_cstride = 192; sp.xh_c0 = 160;
-                sp.dst_h = cat; sp.dst_cstride = 192; sp.dst_c0 = 160;
-                win(sp, base + 1);
-                SR_DO(run_sft(n->rdb_sft[i][j][1], sp, s));
-            }
-            {   // x = conv5(cat) * 0.2 + x
-                ConvParams p = c0; p.src = cat; p.src_cstride = 192; p.src_c0 = 0; p.mode = SRM_TRUNK; p.scale = 0.2f;
-                p.add_f = cur; p.dst_f = tB;
-                rows(p, base);
-                SR_DO(run_conv(n->rdb_conv[i][j][4], p, s));
-                cur = tB;
+    if (fuse) {
+        // Every SFT layer runs in the epilogue of the convolution that produces its input (epilogue_sft): conv_first -> sft0 of
+        // the first dense block, conv4 -> sft1, conv5 -> sft0 of the next block (for the third block of an RRDB: the RRDB
+        // tail first, then the next sft0 or sftbody).  A block's conv5 writes the NEXT block's first 64 concat channels while
+        // other CTAs still read this block's, so the dense blocks alternate between two concat buffers.
+        auto sft_of = [&](int r) -> const SrSft& {                 // sft0 of dense block r (global index), or sftbody after the last
+            return r < nrdb ? n->rdb_sft[r / 3][r % 3][0] : n->sftbody;
+        };
+        auto next_dst = [&](ConvParams& p, int r) {                // where the fused sft0 / sftbody result goes
+            if (r < nrdb) { p.dst_h2 = (r & 1) ? cat2 : cat; p.dst2_cstride = 192; p.dst2_c0 = 0; }
+            else { p.dst_h2 = sbody; p.dst2_cstride = 64; p.dst2_c0 = 0; }
+        };
+        {   // feat = conv_first(x) -> feat, trunk A; xc0 = sft0(feat) -> cat[0:64]
+            ConvParams p = c0; p.src = in16; p.src_cstride = 32; p.src_c0 = 0; p.mode = SRM_TRUNK_SFT; p.scale = 1.f;
+            p.dst_f = feat; p.dst_f2 = tA; p.cond16 = cond16; p.sftw = sft_of(0).frag; p.sft_n = 64; next_dst(p, 0);
+            rows(p, 3 + 5 * nrdb);
+            SR_DO(run_conv(n->conv_first, p, s));
+        }
+        for (int i = 0; i < n->num_block; ++i) {
+            const float* cur = tA;
+            for (int j = 0; j < 3; ++j) {
+                const int r = 3 * i + j, k = nrdb - 1 - r, base = 3 + 5 * k;
+                __half* cc = (r & 1) ? cat2 : cat;
+                for (int c = 0; c < 4; ++c) {   // x{c+1} = lrelu(conv(cat[0:64+32c])) -> cat[64+32c : 96+32c]; conv4 also applies sft1
+                    ConvParams p = c0; p.src = cc; p.src_cstride = 192; p.src_c0 = 0; p.mode = SRM_STORE_F16; p.lrelu = 0.2f;
+                    p.dst_h = cc; p.dst_cstride = 192; p.dst_c0 = 64 + 32 * c;
+                    if (c == 3) { p.mode = SRM_STORE_F16_SFT; p.cond16 = cond16; p.sftw = n->rdb_sft[i][j][1].frag; p.sft_n = 32; }
+                    rows(p, base + 4 - c);
+                    SR_DO(run_conv(n->rdb_conv[i][j][c], p, s));
+                }
+                {   // x = conv5(cat) * 0.2 + x, then the SFT layer(s) that read it
+                    ConvParams p = c0; p.src = cc; p.src_cstride = 192; p.src_c0 = 0; p.scale = 0.2f; p.add_f = cur;
+                    p.cond16 = cond16; p.sft_n = 64;
+                    if (j < 2) {
+                        p.mode = SRM_TRUNK_SFT; p.dst_f = tB; p.sftw = sft_of(r + 1).frag;
+                    } else {            // block tail: out = sft0(x) * 0.2 + x_in -> trunk A, then the next sft0 / sftbody of that
+                        p.mode = SRM_TRUNK_SFT2; p.dst_f = tA; p.add_f2 = tA; p.scale2 = 0.2f;
+                        p.sftw = n->rrdb_sft[i].frag; p.sftw2 = sft_of(r + 1).frag;
+                    }
+                    next_dst(p, r + 1);
+                    rows(p, base);
+                    SR_DO(run_conv(n->rdb_conv[i][j][4], p, s));
+                    cur = tB;
+                }
             }
         }
-        {   // out = sft0(rdb3 out) * 0.2 + x_in  -> A
-            SftParams sp{}; sp.cond = cond32; sp.x_f = tB; sp.dst_f = tA; sp.res_f = tA; sp.res_scale = 0.2f;
-            win(sp, 3 + 5 * (nrdb - 3 * (i + 1)));
-            SR_DO(run_sft(n->rrdb_sft[i], sp, s));
+        {   // body_feat = conv_body(sftbody(trunk)) + feat   (sbody was written by the last conv5)
+            ConvParams p = c0; p.src = sbody; p.src_cstride = 64; p.mode = SRM_ADD_STORE_F16; p.add_f = feat; p.dst_h = bf; p.dst_cstride = 64;
+            rows(p, 2);
+            SR_DO(run_conv(n->conv_body, p, s));
         }
-    }
-    {   // body_feat = conv_body(sftbody(trunk)) + feat
-        SftParams sp{}; sp.cond = cond32; sp.x_f = tA; sp.dst_h = sbody; sp.dst_cstride = 64; sp.dst_c0 = 0;
-        win(sp, 3);
-        SR_DO(run_sft(n->sftbody, sp, s));
-        ConvParams p = c0; p.src = sbody; p.src_cstride = 64; p.mode = SRM_ADD_STORE_F16; p.add_f = feat; p.dst_h = bf; p.dst_cstride = 64;
-        rows(p, 2);
-        SR_DO(run_conv(n->conv_body, p, s));
+    } else {
+        {   // feat = conv_first(x): fp32 into `feat` and into trunk A (the initial trunk)
+            ConvParams p = c0; p.src = in16; p.src_cstride = 32; p.src_c0 = 0; p.mode = SRM_STORE_F32F16; p.dst_f = feat; p.dst_f2 = tA;
+            rows(p, 3 + 5 * nrdb);
+            SR_DO(run_conv(n->conv_first, p, s));
+        }
+        for (int i = 0; i < n->num_block; ++i) {
+            // RRDB_SFT.forward: trunk A holds x (kept for the block's tail), RDBs update A -> B -> B -> B
+            const float* cur = tA;
+            for (int j = 0; j < 3; ++j) {
+                const int k = nrdb - 1 - (3 * i + j);                              // dense blocks still to come
+                const int base = 3 + 5 * k;                                        // rows(base): this block's output
+                {   // xc0 = sft0(x) -> cat[0:64]
+                    SftParams sp{}; sp.cond = cond32; sp.x_f = cur; sp.dst_h = cat; sp.dst_cstride = 192; sp.dst_c0 = 0;
+                    win(sp, base + 5);
+                    SR_DO(run_sft(n->rdb_sft[i][j][0], sp, s));
+                }
+                for (int c = 0; c < 4; ++c) {   // x{c+1} = lrelu(conv(cat[0:64+32c])) -> cat[64+32c : 96+32c]
+                    ConvParams p = c0; p.src = cat; p.src_cstride = 192; p.src_c0 = 0; p.mode = SRM_STORE_F16; p.lrelu = 0.2f;
+                    p.dst_h = cat; p.dst_cstride = 192; p.dst_c0 = 64 + 32 * c;
+                    rows(p, base + 4 - c);
+                    SR_DO(run_conv(n->rdb_conv[i][j][c], p, s));
+                }
+                {   // xc1 = sft1(x4) in place: cat[160:192]
+                    SftParams sp{}; sp.cond = cond32; sp.x_h = cat; sp.xh_cstride = 192; sp.xh_c0 = 160;
+                    sp.dst_h = cat; sp.dst_cstride = 192; sp.dst_c0 = 160;
+                    win(sp, base + 1);
+                    SR_DO(run_sft(n->rdb_sft[i][j][1], sp, s));
+                }
+                {   // x = conv5(cat) * 0.2 + x
+                    ConvParams p = c0; p.src = cat; p.src_cstride = 192; p.src_c0 = 0; p.mode = SRM_TRUNK; p.scale = 0.2f;
+                    p.add_f = cur; p.dst_f = tB;
+                    rows(p, base);
+                    SR_DO(run_conv(n->rdb_conv[i][j][4], p, s));
+                    cur = tB;
+                }
+            }
+            {   // out = sft0(rdb3 out) * 0.2 + x_in  -> A
+                SftParams sp{}; sp.cond = cond32; sp.x_f = tB; sp.dst_f = tA; sp.res_f = tA; sp.res_scale = 0.2f;
+                win(sp, 3 + 5 * (nrdb - 3 * (i + 1)));
+                SR_DO(run_sft(n->rrdb_sft[i], sp, s));
+            }
+        }
+        {   // body_feat = conv_body(sftbody(trunk)) + feat
+            SftParams sp{}; sp.cond = cond32; sp.x_f = tA; sp.dst_h = sbody; sp.dst_cstride = 64; sp.dst_c0 = 0;
+            win(sp, 3);
+            SR_DO(run_sft(n->sftbody, sp, s));
+            ConvParams p = c0; p.src = sbody; p.src_cstride = 64; p.mode = SRM_ADD_STORE_F16; p.add_f = feat; p.dst_h = bf; p.dst_cstride = 64;
+            rows(p, 2);
+            SR_DO(run_conv(n->conv_body, p, s));
+        }
     }
     {   // upsample x2 (nearest) + conv + lrelu, twice; conv_hr + lrelu; conv_last (rows in the layer's own resolution)
         ConvParams p = c0; p.H = 2 * h; p.W = 2 * w; p.upsample = 1; p.src = bf; p.src_cstride = 64; p.mode = SRM_STORE_F16; p.lrelu = 0.2f;

@@ -227,3 +227,22 @@ def test_tile_process_streams_and_pdl_do_not_change_results(net, cuda_device):
     assert torch.equal(a, b) and torch.equal(a, d)
     ref = sftnet.tile_process(sftnet.random_state_dict(seed=3), x.cpu(), c.cpu(), 64, 10)
     assert pipeline.psnr(a.cpu(), ref) >= 60.0
+
+
+def test_fused_sft_epilogues_match_the_separate_sft_passes(net, cuda_device, monkeypatch):
+    """Default: every SFT layer runs in the epilogue of the convolution that produces its input (mma.sync on the accumulator
+    fragments, csrc/k4_sr.cu epilogue_sft); K4_SR_FUSE_SFT=0: 36 separate tcgen05 SFT passes per tile (the round-1
+    structure).  Same operands (fp16 weights / activations), different accumulation order: both within the decoder's bar of
+    the fp32 network and far closer to each other."""
+    g = torch.Generator().manual_seed(77)
+    x = (torch.rand(1, 3, 70, 90, generator=g) * 1.2 - 0.1).to(cuda_device)
+    c = torch.rand(1, 1, 70, 90, generator=g).to(cuda_device)
+    monkeypatch.delenv('K4_SR_FUSE_SFT', raising=False)
+    a = net(x, c).clone()
+    monkeypatch.setenv('K4_SR_FUSE_SFT', '0')
+    b = net(x, c).clone()
+    monkeypatch.delenv('K4_SR_FUSE_SFT', raising=False)
+    ref = sftnet.sftnet_forward(sftnet.random_state_dict(seed=3), x.cpu(), c.cpu())
+    pa, pb, pab = pipeline.psnr(a.cpu(), ref), pipeline.psnr(b.cpu(), ref), pipeline.psnr(a.cpu(), b.cpu())
+    print('fused vs fp32', pa, 'unfused vs fp32', pb, 'fused vs unfused', pab)
+    assert pa >= 60.0 and pb >= 60.0 and pab >= 66.0
