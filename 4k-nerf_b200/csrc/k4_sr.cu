@@ -1400,6 +1400,154 @@ __global__ void __launch_bounds__(128) condnet_kernel(const __grid_constant__ Co
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// CondNet on the tensor cores (round 2): the 1x1 layers (64->64, 64->64, 64->32) as mma.sync GEMMs on 16-pixel row
+// blocks, fp32-class through a 3-term fp16 split (a = ah + al, W = Wh + Wl; ah*Wh + al*Wh + ah*Wl, fp32 accumulate:
+// the dropped al*Wl term is ~2^-22 relative), the 3x3 layer (9 MACs per output) in fp32 FFMA computed directly in the
+// A-fragment layout.  The condition map feeds every SFT layer, so it is kept at fp32 accuracy; the fp32 FFMA kernel
+// above (254 us per 520x520 tile, 4 % of the decoder) stays as the reference (K4_CONDNET_FP32=1).
+// ---------------------------------------------------------------------------------------------
+constexpr int CNM_PITCH = 72;                                   // halfs per weight row (64 + 8: conflict-free fragment loads)
+struct CnmLayout { int w1h, w1l, w2h, w2l, w3h, w3l, w0, b0, b1, b2, b3, total; };
+__host__ __device__ inline CnmLayout cnm_layout() {
+    CnmLayout L; int o = 0;
+    L.w1h = o; o += 64 * CNM_PITCH * 2; L.w1l = o; o += 64 * CNM_PITCH * 2;
+    L.w2h = o; o += 64 * CNM_PITCH * 2; L.w2l = o; o += 64 * CNM_PITCH * 2;
+    L.w3h = o; o += 32 * CNM_PITCH * 2; L.w3l = o; o += 32 * CNM_PITCH * 2;
+    L.w0 = o; o += 64 * 9 * 4; L.b0 = o; o += 64 * 4; L.b1 = o; o += 64 * 4; L.b2 = o; o += 64 * 4; L.b3 = o; o += 32 * 4;
+    L.total = (o + 15) & ~15;
+    return L;
+}
+// w: c0 [64][9], b0[64], c2 [64][64], b2, c4 [64][64], b4, c6 [32][64], b6  (the fp32 kernel's packing)
+__global__ void pack_condnet_mma_kernel(const float* __restrict__ w, unsigned char* __restrict__ dst) {
+    const CnmLayout L = cnm_layout();
+    const float* c0 = w; const float* b0 = c0 + 576; const float* c2 = b0 + 64; const float* b2 = c2 + 4096;
+    const float* c4 = b2 + 64; const float* b4 = c4 + 4096; const float* c6 = b4 + 64; const float* b6 = c6 + 2048;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    auto split = [&](int offh, int offl, int n, int k, float v) {
+        const __half hi = __float2half_rn(v);
+        reinterpret_cast<__half*>(dst + offh)[n * CNM_PITCH + k] = hi;
+        reinterpret_cast<__half*>(dst + offl)[n * CNM_PITCH + k] = __float2half_rn(v - __half2float(hi));
+    };
+    if (i < 4096) { split(L.w1h, L.w1l, i >> 6, i & 63, c2[i]); split(L.w2h, L.w2l, i >> 6, i & 63, c4[i]); }
+    if (i < 2048) split(L.w3h, L.w3l, i >> 6, i & 63, c6[i]);
+    if (i < 576) reinterpret_cast<float*>(dst + L.w0)[i] = c0[i];
+    if (i < 64) { reinterpret_cast<float*>(dst + L.b0)[i] = b0[i]; reinterpret_cast<float*>(dst + L.b1)[i] = b2[i]; reinterpret_cast<float*>(dst + L.b2)[i] = b4[i]; }
+    if (i < 32) reinterpret_cast<float*>(dst + L.b3)[i] = b6[i];
+}
+
+struct CondMmaParams { const float* cond_in; const unsigned char* wblk; float* cond_out; __half* cond16; int H, W, y_lo, y_hi; };
+
+// accumulator fragments of 2 adjacent n8 blocks -> hi / lo A fragments of one k16 step
+__device__ __forceinline__ void cnm_split_frag(const float (&c0)[4], const float (&c1)[4], uint32_t (&ah)[4], uint32_t (&al)[4]) {
+    auto pk = [](float x, float y, uint32_t& hi, uint32_t& lo) {
+        const __half2 h = __floats2half2_rn(x, y);
+        const float2 hf = __half22float2(h);
+        const __half2 l = __floats2half2_rn(x - hf.x, y - hf.y);
+        hi = *reinterpret_cast<const uint32_t*>(&h); lo = *reinterpret_cast<const uint32_t*>(&l);
+    };
+    pk(c0[0], c0[1], ah[0], al[0]); pk(c0[2], c0[3], ah[1], al[1]);
+    pk(c1[0], c1[1], ah[2], al[2]); pk(c1[2], c1[3], ah[3], al[3]);
+}
+// one 64-input layer for 16 pixels: NBLK n8 blocks of outputs, 3-term split products
+template <int NBLK>
+__device__ __forceinline__ void cnm_layer(const unsigned char* sm, int offh, int offl, int offb, const uint32_t (&ah)[4][4], const uint32_t (&al)[4][4],
+                                          int g, int tq, float (&c)[NBLK][4]) {
+    const __half* Wh = reinterpret_cast<const __half*>(sm + offh);
+    const __half* Wl = reinterpret_cast<const __half*>(sm + offl);
+    const float* b = reinterpret_cast<const float*>(sm + offb);
+#pragma unroll
+    for (int j = 0; j < NBLK; ++j) {
+        c[j][0] = c[j][2] = b[8 * j + 2 * tq]; c[j][1] = c[j][3] = b[8 * j + 2 * tq + 1];
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+            const __half* wh = Wh + (8 * j + g) * CNM_PITCH + 16 * ks + 2 * tq;
+            const __half* wl = Wl + (8 * j + g) * CNM_PITCH + 16 * ks + 2 * tq;
+            const uint32_t bh0 = *reinterpret_cast<const uint32_t*>(wh), bh1 = *reinterpret_cast<const uint32_t*>(wh + 8);
+            sr_hmma(c[j], al[ks], bh0, bh1);                     // small terms first
+            sr_hmma(c[j], ah[ks], *reinterpret_cast<const uint32_t*>(wl), *reinterpret_cast<const uint32_t*>(wl + 8));
+            sr_hmma(c[j], ah[ks], bh0, bh1);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128) condnet_mma_kernel(const __grid_constant__ CondMmaParams p) {
+    extern __shared__ __align__(16) unsigned char csm[];
+    const CnmLayout L = cnm_layout();
+    for (int i = threadIdx.x; i < L.total / 16; i += blockDim.x) reinterpret_cast<uint4*>(csm)[i] = __ldg(reinterpret_cast<const uint4*>(p.wblk) + i);
+    __syncthreads();
+    SR_PDL_SYNC();
+    const int lane = threadIdx.x & 31, g = lane >> 2, tq = lane & 3;
+    const long long p0 = (long long)p.y_lo * p.W, pend = (long long)p.y_hi * p.W;
+    const long long nblk = (pend - p0 + 15) / 16;
+    const float* W0 = reinterpret_cast<const float*>(csm + L.w0);
+    const float* B0 = reinterpret_cast<const float*>(csm + L.b0);
+    for (long long blk = (long long)blockIdx.x * 4 + (threadIdx.x >> 5); blk < nblk; blk += (long long)gridDim.x * 4) {
+        const long long pixA = p0 + blk * 16 + g, pixB = pixA + 8;
+        const bool inA = pixA < pend, inB = pixB < pend;
+        // 3x3 neighbourhoods of the two pixels (zero padding at the tile border, as the reference's conv)
+        float nA[9], nB[9];
+        {
+            const long long pa = inA ? pixA : p0, pb = inB ? pixB : p0;
+            const int ya = (int)(pa / p.W), xa = (int)(pa - (long long)ya * p.W), yb = (int)(pb / p.W), xb = (int)(pb - (long long)yb * p.W);
+#pragma unroll
+            for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+                for (int dx = 0; dx < 3; ++dx) {
+                    const int y1 = ya + dy - 1, x1 = xa + dx - 1, y2 = yb + dy - 1, x2 = xb + dx - 1;
+                    nA[dy * 3 + dx] = (y1 >= 0 && y1 < p.H && x1 >= 0 && x1 < p.W) ? __ldg(p.cond_in + (size_t)y1 * p.W + x1) : 0.f;
+                    nB[dy * 3 + dx] = (y2 >= 0 && y2 < p.H && x2 >= 0 && x2 < p.W) ? __ldg(p.cond_in + (size_t)y2 * p.W + x2) : 0.f;
+                }
+        }
+        // layer 0 (3x3, 1 -> 64) in fp32, each thread the 16 channels of its A-fragment slots: k-step ks holds channels
+        // 16ks + 2tq, +1 (regs 0 / 1: pixel A / B) and 16ks + 8 + 2tq, +1 (regs 2 / 3)
+        uint32_t ah[4][4], al[4][4];
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+            float va[4], vb[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int ch = 16 * ks + (e >> 1) * 8 + 2 * tq + (e & 1);
+                float a = B0[ch], b = B0[ch];
+#pragma unroll
+                for (int k = 0; k < 9; ++k) { a = fmaf(W0[ch * 9 + k], nA[k], a); b = fmaf(W0[ch * 9 + k], nB[k], b); }
+                va[e] = fmaxf(a, 0.2f * a); vb[e] = fmaxf(b, 0.2f * b);
+            }
+            const float c0[4] = {va[0], va[1], vb[0], vb[1]}, c1[4] = {va[2], va[3], vb[2], vb[3]};
+            cnm_split_frag(c0, c1, ah[ks], al[ks]);
+        }
+        float c[8][4];
+        cnm_layer<8>(csm, L.w1h, L.w1l, L.b1, ah, al, g, tq, c);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) c[j][e] = fmaxf(c[j][e], 0.2f * c[j][e]);
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) cnm_split_frag(c[2 * ks], c[2 * ks + 1], ah[ks], al[ks]);
+        cnm_layer<8>(csm, L.w2h, L.w2l, L.b2, ah, al, g, tq, c);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) c[j][e] = fmaxf(c[j][e], 0.2f * c[j][e]);
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) cnm_split_frag(c[2 * ks], c[2 * ks + 1], ah[ks], al[ks]);
+        float o[4][4];
+        cnm_layer<4>(csm, L.w3h, L.w3l, L.b3, ah, al, g, tq, o);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int ch = 8 * j + 2 * tq;
+            if (inA) {
+                *reinterpret_cast<float2*>(p.cond_out + pixA * 32 + ch) = make_float2(o[j][0], o[j][1]);
+                if (p.cond16) *reinterpret_cast<__half2*>(p.cond16 + pixA * 32 + ch) = __floats2half2_rn(o[j][0], o[j][1]);
+            }
+            if (inB) {
+                *reinterpret_cast<float2*>(p.cond_out + pixB * 32 + ch) = make_float2(o[j][2], o[j][3]);
+                if (p.cond16) *reinterpret_cast<__half2*>(p.cond16 + pixB * 32 + ch) = __floats2half2_rn(o[j][2], o[j][3]);
+            }
+        }
+    }
+}
+
 // planar fp32 [C,H,W] -> NHWC fp16 [H,W,32] (zero padded)
 __global__ void nchw_to_nhwc32_kernel(const float* __restrict__ src, __half* __restrict__ dst, int C, long long P) {
     SR_PDL_SYNC();
@@ -1496,6 +1644,7 @@ struct k4_srnet {
     SrSft rrdb_sft[32];
     SrSft sftbody;
     float* condnet_w;
+    unsigned char* condnet_mma;                 // cnm_layout block of condnet_mma_kernel
     void* allocs[1024];
     int n_allocs;
     size_t bytes;
@@ -1861,6 +2010,10 @@ extern "C" int k4_srnet_create(const k4_srnet_desc* d, k4_stream_t stream, k4_sr
         const size_t cnt[8] = {576, 64, 4096, 64, 4096, 64, 2048, 32};
         for (int q = 0; q < 8; ++q) { cudaMemcpyAsync(dd, P[k + q], cnt[q] * 4, cudaMemcpyDeviceToDevice, s); dd += cnt[q]; }
         k += 8;
+        SR_TRY(sr_alloc(n, (void**)&n->condnet_mma, (size_t)cnm_layout().total));
+        K4_CUDA_TRY(cudaMemsetAsync(n->condnet_mma, 0, cnm_layout().total, s));
+        pack_condnet_mma_kernel<<<16, 256, 0, s>>>(n->condnet_w, n->condnet_mma);
+        K4_CUDA_TRY(cudaGetLastError());
     }
     for (int i = 0; i < d->num_block; ++i) {
         for (int j = 0; j < 3; ++j) {
@@ -1941,11 +2094,23 @@ extern "C" int k4_srnet_forward_roi(const k4_srnet* n, const float* d_x, const f
     K4_CUDA_TRY(sr_launch(nchw_to_nhwc32_kernel, (unsigned)((P * 32 + 255) / 256), 256, 0, s, d_x, in16, 3, P));
     {
         const SrRows rr = sr_rows(ky0, ky1, 3 + 5 * nrdb + 5, h);          // every SFT layer inside the window reads it
-        CondParams cp{d_cond, n->condnet_w, cond32, h, w, rr.lo, rr.hi, fuse ? cond16 : nullptr};
-        constexpr int NW = 64 * 9 + 64 + 2 * (64 * 64 + 64) + 32 * 64 + 32;
-        SR_DO(sr_set_smem(condnet_kernel, 11, NW * 4));
-        const long long np = (long long)(rr.hi - rr.lo) * w;
-        K4_CUDA_TRY(sr_launch(condnet_kernel, (unsigned)((np + 127) / 128), 128, (size_t)NW * 4, s, cp));
+        const char* cenv = getenv("K4_CONDNET_FP32");
+        if (cenv && cenv[0] == '1') {
+            CondParams cp{d_cond, n->condnet_w, cond32, h, w, rr.lo, rr.hi, fuse ? cond16 : nullptr};
+            constexpr int NW = 64 * 9 + 64 + 2 * (64 * 64 + 64) + 32 * 64 + 32;
+            SR_DO(sr_set_smem(condnet_kernel, 11, NW * 4));
+            const long long np = (long long)(rr.hi - rr.lo) * w;
+            K4_CUDA_TRY(sr_launch(condnet_kernel, (unsigned)((np + 127) / 128), 128, (size_t)NW * 4, s, cp));
+        } else {
+            CondMmaParams cp{d_cond, n->condnet_mma, cond32, fuse ? cond16 : nullptr, h, w, rr.lo, rr.hi};
+            const int smem = cnm_layout().total;
+            SR_DO(sr_set_smem(condnet_mma_kernel, 12, smem));
+            const long long nb = ((long long)(rr.hi - rr.lo) * w + 15) / 16;
+            long long grid = (nb + 3) / 4;
+            const long long cap = (long long)sr_dev()->sms * 4;
+            if (grid > cap) grid = cap;
+            K4_CUDA_TRY(sr_launch(condnet_mma_kernel, (unsigned)(grid < 1 ? 1 : grid), 128, (size_t)smem, s, cp));
+        }
     }
     ConvParams c0{};
     c0.H = h; c0.W = w;
