@@ -328,6 +328,19 @@ def main():
 
     for i in range(max(args.warmup, 3)):
         step(i)
+    gather_ms = None
+    if world > 1:
+        # NCCL sets up its channels lazily: a few more gathers of the frame before the clock starts, and their time on its own
+        for _ in range(5):
+            frame.gather()
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for _ in range(5):
+            frame.gather()
+        g1.record()
+        torch.cuda.synchronize()
+        gather_ms = g0.elapsed_time(g1) / 5
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -431,6 +444,7 @@ def main():
                       'ws': 'f32 geometry/interpolation/compositing; rgbnet f16 operands, f32 accumulate (tcgen05)'}[mode],
             'data': 'synthetic', 'config': workload_config(args, world), 'mlp_mode': mode,
             'e2e': e2e, 'gpu_launches': args.steps, 'clocks': clocks,
+            **({'gather_unpack_ms_rank0': gather_ms} if gather_ms is not None else {}),
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
                          'traffic': traffic, 'peak_source': peak_src,
                          'kernel': kernel_name,
