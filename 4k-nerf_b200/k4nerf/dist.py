@@ -34,20 +34,26 @@ def cyclic_pad_rows(H, world_size, block=ROW_BLOCK):
     return ((nblk + world_size - 1) // world_size) * block
 
 
-def unpack_frame_cyclic(gathered, H, W, world_size, block=ROW_BLOCK):
+def unpack_frame_cyclic(gathered, H, W, world_size, block=ROW_BLOCK, out=None):
     """[world, 5 * n_pad] (block-cyclic bands) -> dict of full-frame tensors in image order.
     Image block b sits at local block b // world of rank b % world, so image order is the (local block,
-    rank) transpose of the gathered buffer: one strided copy per quantity, no index kernels."""
+    rank) transpose of the gathered buffer: one strided copy per quantity, no index kernels.
+    ``out``: a ``[5 * world * n_pad]`` float buffer the three copies land in (the returned tensors are views
+    of it, valid until it is written again); without it every call allocates the frame anew."""
     rows_pad = cyclic_pad_rows(H, world_size, block)
     n_pad = rows_pad * W
     nlb = rows_pad // block
     g = gathered.view(world_size, 5 * n_pad)
+    if out is None:
+        out = torch.empty(5 * world_size * n_pad, device=gathered.device, dtype=gathered.dtype)
+    n_full = world_size * n_pad
 
-    def image_order(x, c):          # x: [world, rows_pad * W * c]
-        return x.reshape(world_size, nlb, block * W * c).transpose(0, 1).reshape(-1)[:H * W * c]
-    rgb = image_order(g[:, :3 * n_pad], 3).view(H * W, 3)
-    depth = image_order(g[:, 3 * n_pad:4 * n_pad], 1)
-    ainv = image_order(g[:, 4 * n_pad:5 * n_pad], 1)
+    def image_order(x, c, dst):     # x: [world, rows_pad * W * c] -> dst: [nlb, world, block * W * c]
+        dst.view(nlb, world_size, block * W * c).copy_(x.reshape(world_size, nlb, block * W * c).transpose(0, 1))
+        return dst[:H * W * c]
+    rgb = image_order(g[:, :3 * n_pad], 3, out[:3 * n_full]).view(H * W, 3)
+    depth = image_order(g[:, 3 * n_pad:4 * n_pad], 1, out[3 * n_full:4 * n_full])
+    ainv = image_order(g[:, 4 * n_pad:5 * n_pad], 1, out[4 * n_full:5 * n_full])
     return {'rgb_marched': rgb, 'depth': depth, 'alphainv_last': ainv}
 
 
@@ -112,11 +118,16 @@ class CyclicFrame:
         self.buf = torch.zeros(5 * self.n_pad, device=device, dtype=torch.float32)
         self.out = packed_band_views(self.buf, self.n_band, self.n_pad)
         self.gathered = torch.empty(self.world * 5 * self.n_pad, device=device, dtype=torch.float32) if self.world > 1 else self.buf
+        # image-order frame, allocated once: a gather per step must not reach the allocator (a cudaMalloc inside a step
+        # synchronises the device, and with NCCL's peer mappings in place it is slow)
+        self.full = torch.empty(self.world * 5 * self.n_pad, device=device, dtype=torch.float32)
 
     def gather(self):
+        """All-gather + image-order transpose.  The returned tensors are views of this object's frame buffer: they hold
+        the frame until the next ``gather()`` (clone to keep one longer)."""
         if self.world > 1:
             dist.all_gather_into_tensor(self.gathered, self.buf, group=self.group)
-        return unpack_frame_cyclic(self.gathered, self.H, self.W, self.world)
+        return unpack_frame_cyclic(self.gathered, self.H, self.W, self.world, out=self.full)
 
     def render(self, make_rays, render_fn):
         if self.k > 0:

@@ -136,7 +136,9 @@ def render_frame_4k_sharded(model, net_sr, H, W, K, c2w, ndc, render_kwargs, tes
     replicated): every rank marches its 8-row blocks of the LR frame
     (one all-gather of the packed ``[rgb|depth|alphainv]`` rows), then decodes its share of the
     reference tiles / tile row-parts (one all-gather of the x4 blocks).  Every rank returns the full
-    frame; values are identical to the single-GPU :func:`render_frame_4k`."""
+    frame; values are identical to the single-GPU :func:`render_frame_4k`.  The LR dict's tensors are views of the
+    cached :class:`k4nerf.dist.CyclicFrame` buffer (no allocation per frame): valid until the next call with the same
+    (H, W, group)."""
     from . import dist as kdist
     kw = dict(render_kwargs)
     kw['render_depth'] = True
