@@ -431,14 +431,25 @@ extern "C" int k4_scene_create(const k4_scene_desc* d, k4_stream_t stream, k4_sc
 // ------------------------------------------------------------------------------------------------
 extern "C" size_t k4_render_workspace_bytes(const k4_scene*, int64_t) { return 256; }
 
-extern "C" int k4_render_rays(const k4_scene* sc, const k4_render_args* a,
-                              const float* d_rays_o, const float* d_rays_d, const float* d_viewdirs,
-                              int64_t n_rays, const k4_render_out* out,
-                              void* d_workspace, size_t workspace_bytes, k4_stream_t stream) {
-    if (!sc || !a || !out) return K4_ERR_INVALID_ARG;
+static int render_impl(const k4_scene* sc, const k4_render_args* a,
+                       const float* d_rays_o, const float* d_rays_d, const float* d_viewdirs,
+                       int64_t n_rays, const k4_render_out* out, const k4_frame_dst* fd,
+                       void* d_workspace, size_t workspace_bytes, k4_stream_t stream) {
+    static const k4_render_out no_out = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    if (!sc || !a || (!out && !fd)) return K4_ERR_INVALID_ARG;
+    if (!out) out = &no_out;
     if (n_rays < 0) return K4_ERR_INVALID_ARG;
     if (n_rays == 0) return K4_OK;
-    if (!d_rays_o || !d_rays_d || !out->d_rgb_marched || !out->d_alphainv_last) return K4_ERR_INVALID_ARG;
+    if (!d_rays_o || !d_rays_d) return K4_ERR_INVALID_ARG;
+    if (!fd && (!out->d_rgb_marched || !out->d_alphainv_last)) return K4_ERR_INVALID_ARG;
+    if (fd) {
+        if (fd->n_dst < 1 || fd->n_dst > K4_MAX_PEERS || fd->world < 1 || fd->rank < 0 || fd->rank >= fd->world ||
+            fd->frame_w < 1 || n_rays % fd->frame_w != 0) return K4_ERR_INVALID_ARG;
+        for (int i = 0; i < fd->n_dst; ++i) if (!fd->d_frame[i]) return K4_ERR_INVALID_ARG;
+        const long long r = n_rays / fd->frame_w - 1;                       // last local row -> its image row must fit
+        const long long g = ((r >> 3) * fd->world + fd->rank) * 8 + (r & 7);
+        if ((g + 1) * fd->frame_w > fd->n_full) return K4_ERR_INVALID_ARG;
+    }
     if (sc->dev.depth > 0 && !d_viewdirs) return K4_ERR_INVALID_ARG;
     if (!d_workspace || workspace_bytes < k4_render_workspace_bytes(sc, n_rays)) return K4_ERR_WORKSPACE;
     if (!(a->stepsize > 0.f)) return K4_ERR_INVALID_ARG;
@@ -451,7 +462,7 @@ extern "C" int k4_render_rays(const k4_scene* sc, const k4_render_args* a,
     memset(&rp, 0, sizeof(rp));
     rp.near_ = a->near_;
     rp.bg = a->bg;
-    rp.render_depth = a->render_depth && out->d_depth;
+    rp.render_depth = a->render_depth && (fd || out->d_depth);
     if (v.kind == K4_KIND_DVGO) {
         rp.far_ = 1e9f;                                            // lib/dvgo.py:307
         rp.stepdist = a->stepsize * v.voxel_size;                   // lib/dvgo.py:310 (fp32 product)
@@ -481,6 +492,10 @@ extern "C" int k4_render_rays(const k4_scene* sc, const k4_render_args* a,
     rp.rays_o = d_rays_o; rp.rays_d = d_rays_d; rp.viewdirs = d_viewdirs;
     rp.rgb = out->d_rgb_marched; rp.depth = rp.render_depth ? out->d_depth : nullptr;
     rp.alphainv = out->d_alphainv_last;
+    if (fd) {
+        rp.n_dst = fd->n_dst; rp.f_rank = fd->rank; rp.f_world = fd->world; rp.f_w = fd->frame_w; rp.f_nfull = fd->n_full;
+        for (int i = 0; i < fd->n_dst; ++i) rp.d_frame[i] = fd->d_frame[i];
+    }
     rp.ray_stats = out->d_ray_stats; rp.t_minmax = out->d_t_minmax; rp.counters = out->d_counters;
     rp.tile_counter = reinterpret_cast<unsigned int*>(d_workspace);
     K4_CUDA_TRY(cudaMemsetAsync(d_workspace, 0, 16, s));
@@ -489,6 +504,62 @@ extern "C" int k4_render_rays(const k4_scene* sc, const k4_render_args* a,
         return k4_ws_supported(v) ? k4_launch_march_ws(sc, rp, s) : K4_ERR_UNSUPPORTED;
     }
     return k4_launch_march(sc, rp, a->mlp_mode, s);
+}
+
+extern "C" int k4_render_rays(const k4_scene* sc, const k4_render_args* a,
+                              const float* d_rays_o, const float* d_rays_d, const float* d_viewdirs,
+                              int64_t n_rays, const k4_render_out* out,
+                              void* d_workspace, size_t workspace_bytes, k4_stream_t stream) {
+    if (!out) return K4_ERR_INVALID_ARG;
+    return render_impl(sc, a, d_rays_o, d_rays_d, d_viewdirs, n_rays, out, nullptr, d_workspace, workspace_bytes, stream);
+}
+
+extern "C" int k4_render_rays_frames(const k4_scene* sc, const k4_render_args* a,
+                                     const float* d_rays_o, const float* d_rays_d, const float* d_viewdirs,
+                                     int64_t n_rays, const k4_frame_dst* dst, const k4_render_out* out,
+                                     void* d_workspace, size_t workspace_bytes, k4_stream_t stream) {
+    if (!dst) return K4_ERR_INVALID_ARG;
+    return render_impl(sc, a, d_rays_o, d_rays_d, d_viewdirs, n_rays, out, dst, d_workspace, workspace_bytes, stream);
+}
+
+// ---- device memory shared between the ranks of a node (CUDA IPC; one process per GPU) ----
+extern "C" int k4_peer_alloc(size_t bytes, void** d_ptr) {
+    if (!d_ptr || bytes == 0) return K4_ERR_INVALID_ARG;
+    *d_ptr = nullptr;
+    void* p = nullptr;
+    K4_CUDA_TRY(cudaMalloc(&p, bytes));
+    cudaError_t e = cudaMemset(p, 0, bytes);
+    if (e != cudaSuccess) { cudaFree(p); k4_set_cuda_error(e, "cudaMemset(peer buffer)"); return K4_ERR_CUDA; }
+    *d_ptr = p;
+    return K4_OK;
+}
+extern "C" int k4_peer_free(void* d_ptr) {
+    if (!d_ptr) return K4_OK;
+    K4_CUDA_TRY(cudaFree(d_ptr));
+    return K4_OK;
+}
+extern "C" int k4_peer_export(void* d_ptr, unsigned char handle[64]) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
+    if (!d_ptr || !handle) return K4_ERR_INVALID_ARG;
+    cudaIpcMemHandle_t h;
+    K4_CUDA_TRY(cudaIpcGetMemHandle(&h, d_ptr));
+    memcpy(handle, &h, 64);
+    return K4_OK;
+}
+extern "C" int k4_peer_open(const unsigned char handle[64], void** d_ptr) {
+    if (!d_ptr || !handle) return K4_ERR_INVALID_ARG;
+    *d_ptr = nullptr;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    void* p = nullptr;
+    K4_CUDA_TRY(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    *d_ptr = p;
+    return K4_OK;
+}
+extern "C" int k4_peer_close(void* d_ptr) {
+    if (!d_ptr) return K4_OK;
+    K4_CUDA_TRY(cudaIpcCloseMemHandle(d_ptr));
+    return K4_OK;
 }
 
 extern "C" int k4_make_rays_rows(const float* h_K, const float* h_c2w, int32_t H, int32_t W, int32_t ndc,

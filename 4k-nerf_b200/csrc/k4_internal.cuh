@@ -102,6 +102,13 @@ struct K4RenderParams {
     float* t_minmax;
     unsigned long long* counters;
     unsigned int* tile_counter;
+    // k4_render_rays_frames (multi-GPU frame output): n_dst > 0 -> rgb / depth / alphainv above are unused and the ray of
+    // local row r, column c is stored at ray index g = (((r >> 3) * f_world + f_rank) * 8 + (r & 7)) * f_w + c of every
+    // frame d_frame[0 .. n_dst) (the local one and the peer-mapped ones): rgb at 3g, depth at 3 f_nfull + g, alphainv
+    // at 4 f_nfull + g
+    int n_dst, f_rank, f_world, f_w;
+    long long f_nfull;
+    float* d_frame[K4_MAX_PEERS];
 };
 
 // error plumbing (k4_capi.cu)

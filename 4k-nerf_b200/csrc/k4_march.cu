@@ -279,11 +279,7 @@ k4_march_kernel(const __grid_constant__ K4Dev s, const __grid_constant__ K4Rende
         if (have_ray) {
             // rgb_marched = rgb_feature + alphainv_last * bg   (lib/dvgo.py:425-427)
             const float bgt = __fmul_rn(T, rp.bg);
-            rp.rgb[3 * ray_i + 0] = __fadd_rn(acc_r, bgt);
-            rp.rgb[3 * ray_i + 1] = __fadd_rn(acc_g, bgt);
-            rp.rgb[3 * ray_i + 2] = __fadd_rn(acc_b, bgt);
-            rp.alphainv[ray_i] = T;
-            if (rp.depth) rp.depth[ray_i] = acc_depth;
+            k4_store_ray(rp, ray_i, __fadd_rn(acc_r, bgt), __fadd_rn(acc_g, bgt), __fadd_rn(acc_b, bgt), T, acc_depth);
             if (rp.ray_stats) {
                 int4 st = make_int4(r.n_steps, cnt_m, cnt_d, cnt_c);
                 reinterpret_cast<int4*>(rp.ray_stats)[ray_i] = st;

@@ -227,4 +227,27 @@ __device__ __noinline__ void mlp_fp32(const K4Dev& s, const float* x, float rgb[
     }
 }
 
+// One ray's results: into the caller's [N,3] / [N] arrays, or -- for a block-cyclic multi-GPU frame -- straight into the
+// image-order frame of every rank (peer-mapped stores over NVLink; 20 bytes per ray and destination, issued while the
+// other warps of the CTA march on, so the exchange costs no step of its own).
+__device__ __forceinline__ void k4_store_ray(const K4RenderParams& rp, long long ray_i, float cr, float cg, float cb,
+                                             float T, float depth) {
+    if (rp.n_dst == 0) {
+        rp.rgb[3 * ray_i + 0] = cr; rp.rgb[3 * ray_i + 1] = cg; rp.rgb[3 * ray_i + 2] = cb;
+        rp.alphainv[ray_i] = T;
+        if (rp.depth) rp.depth[ray_i] = depth;
+        return;
+    }
+    const long long row = ray_i / rp.f_w;
+    const long long col = ray_i - row * rp.f_w;
+    const long long g = (((row >> 3) * rp.f_world + rp.f_rank) * 8 + (row & 7)) * rp.f_w + col;
+#pragma unroll 1
+    for (int p = 0; p < rp.n_dst; ++p) {
+        float* f = rp.d_frame[p];
+        f[3 * g + 0] = cr; f[3 * g + 1] = cg; f[3 * g + 2] = cb;
+        if (rp.render_depth) f[3 * rp.f_nfull + g] = depth;
+        f[4 * rp.f_nfull + g] = T;
+    }
+}
+
 }  // namespace

@@ -606,11 +606,8 @@ k4_march_ws_kernel(const __grid_constant__ K4Dev s, const __grid_constant__ K4Re
             named_bar(wg + 1);
             if (have_ray) {
                 const float bgt = __fmul_rn(T, rp.bg);
-                rp.rgb[3 * ray_i + 0] = __fadd_rn(racc[wt * 3 + 0], bgt);
-                rp.rgb[3 * ray_i + 1] = __fadd_rn(racc[wt * 3 + 1], bgt);
-                rp.rgb[3 * ray_i + 2] = __fadd_rn(racc[wt * 3 + 2], bgt);
-                rp.alphainv[ray_i] = T;
-                if (rp.depth) rp.depth[ray_i] = acc_depth;
+                k4_store_ray(rp, ray_i, __fadd_rn(racc[wt * 3 + 0], bgt), __fadd_rn(racc[wt * 3 + 1], bgt),
+                             __fadd_rn(racc[wt * 3 + 2], bgt), T, acc_depth);
                 if (rp.ray_stats) reinterpret_cast<int4*>(rp.ray_stats)[ray_i] = make_int4(r.n_steps, cnt_m, cnt_d, cnt_c);
                 if (rp.t_minmax) { rp.t_minmax[2 * ray_i] = r.t_min; rp.t_minmax[2 * ray_i + 1] = r.t_max; }
             }

@@ -129,11 +129,20 @@ struct ConvParams {
     // SRM_OUT_NCHW: output pixel (y, x) of channel c goes to out_nchw[c*out_ps + (y-crop_y0)*out_rs + (x-crop_x0)] when it lies
     // in the crop window [crop_y0,crop_y1) x [crop_x0,crop_x1) (the kept block of a tile, written straight into the frame)
     long long out_ps, out_rs; int crop_y0, crop_y1, crop_x0, crop_x1;
+    // ... and at the same offset into out_extra[0 .. n_out_extra): the same window of the other ranks' frames (peer-mapped,
+    // k4_srnet_forward_roi_peers) -- the multi-GPU exchange as NVLink stores of the kernel that produces the pixels
+    int n_out_extra; float* out_extra[K4_MAX_PEERS - 1];
     // fused SFT epilogues (SRM_*_SFT*): fp16 condition map [P,32], the fragment-ordered operand blocks of the SFT layer(s)
     // (sft_frag_layout), the fp16 destination of the (last) modulated result, the RRDB input for the block tail
     const __half* cond16; const unsigned char* sftw; const unsigned char* sftw2; int sft_n;
     __half* dst_h2; int dst2_cstride, dst2_c0; const float* add_f2; float scale2;
 };
+
+__device__ __forceinline__ void sr_store_out(const ConvParams& p, long long idx, float v) {
+    p.out_nchw[idx] = v;
+#pragma unroll 1
+    for (int e = 0; e < p.n_out_extra; ++e) p.out_extra[e][idx] = v;
+}
 
 // SFT operands for the in-epilogue mma.sync evaluation: fp16 weights W0 [64][32] (scale_conv0 rows then shift_conv0 rows),
 // W1s [n][32], W1h [n][32] with 40-half row pitch (conflict-free fragment loads), then fp32 biases b0 [64], b1s + 1 [n], b1h [n].
@@ -378,7 +387,7 @@ __global__ void __launch_bounds__(128) conv3x3_tc_kernel(const __grid_constant__
 #pragma unroll
             for (int j = 0; j < 16; ++j)
                 if (c16 * 16 + j < p.n_valid && py >= p.crop_y0 && py < p.crop_y1 && px >= p.crop_x0 && px < p.crop_x1)
-                    p.out_nchw[(long long)(c16 * 16 + j) * p.out_ps + (long long)(py - p.crop_y0) * p.out_rs + (px - p.crop_x0)] = o[j];
+                    sr_store_out(p, (long long)(c16 * 16 + j) * p.out_ps + (long long)(py - p.crop_y0) * p.out_rs + (px - p.crop_x0), o[j]);
         }
     }
     }
@@ -805,7 +814,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv3x3_ws_kernel(const __grid_
 #pragma unroll
                         for (int j = 0; j < 16; ++j)
                             if (c16 * 16 + j < p.n_valid)
-                                p.out_nchw[(long long)(c16 * 16 + j) * p.out_ps + (long long)(oy - p.crop_y0) * p.out_rs + (ox - p.crop_x0)] = o[j];
+                                sr_store_out(p, (long long)(c16 * 16 + j) * p.out_ps + (long long)(oy - p.crop_y0) * p.out_rs + (ox - p.crop_x0), o[j]);
                     }
                 }
             }
@@ -1007,7 +1016,7 @@ __global__ void __launch_bounds__(K64_THREADS, 1) conv3x3_k64_kernel(const __gri
 #pragma unroll
                         for (int j = 0; j < 16; ++j)
                             if (c16 * 16 + j < p.n_valid)
-                                p.out_nchw[(long long)(c16 * 16 + j) * p.out_ps + (long long)(oys[u] - p.crop_y0) * p.out_rs + (oxs[u] - p.crop_x0)] = o[j];
+                                sr_store_out(p, (long long)(c16 * 16 + j) * p.out_ps + (long long)(oys[u] - p.crop_y0) * p.out_rs + (oxs[u] - p.crop_x0), o[j]);
                     }
                 }
             }
@@ -2064,11 +2073,14 @@ static inline SrRows sr_rows(int ky0, int ky1, int r, int h) {
     SrRows o; o.lo = ky0 - r < 0 ? 0 : ky0 - r; o.hi = ky1 + r > h ? h : ky1 + r; return o;
 }
 
-extern "C" int k4_srnet_forward_roi(const k4_srnet* n, const float* d_x, const float* d_cond, int32_t h, int32_t w,
-                                    int32_t keep_y0, int32_t keep_y1, int32_t keep_x0, int32_t keep_x1,
-                                    float* d_out, int64_t out_plane_stride, int64_t out_row_stride,
-                                    void* d_ws, size_t ws_bytes, k4_stream_t stream) {
+static int srnet_forward_roi_impl(const k4_srnet* n, const float* d_x, const float* d_cond, int32_t h, int32_t w,
+                                  int32_t keep_y0, int32_t keep_y1, int32_t keep_x0, int32_t keep_x1,
+                                  float* d_out, int64_t out_plane_stride, int64_t out_row_stride,
+                                  int32_t n_extra, float* const* h_extra,
+                                  void* d_ws, size_t ws_bytes, k4_stream_t stream) {
     if (!n || !d_x || !d_cond || !d_out || h <= 0 || w <= 0) return K4_ERR_INVALID_ARG;
+    if (n_extra < 0 || n_extra > K4_MAX_PEERS - 1 || (n_extra > 0 && !h_extra)) return K4_ERR_INVALID_ARG;
+    for (int e = 0; e < n_extra; ++e) if (!h_extra[e]) return K4_ERR_INVALID_ARG;
     if (keep_y0 < 0 || keep_y1 > h || keep_y0 >= keep_y1 || keep_x0 < 0 || keep_x1 > w || keep_x0 >= keep_x1) return K4_ERR_INVALID_ARG;
     const SrWs L = sr_ws(h, w);
     if (!d_ws || ws_bytes < L.total) return K4_ERR_WORKSPACE;
@@ -2245,10 +2257,29 @@ extern "C" int k4_srnet_forward_roi(const k4_srnet* n, const float* d_x, const f
         q.y_lo = 4 * ky0; q.y_hi = 4 * ky1;
         q.out_ps = out_plane_stride; q.out_rs = out_row_stride;
         q.crop_y0 = 4 * ky0; q.crop_y1 = 4 * ky1; q.crop_x0 = 4 * keep_x0; q.crop_x1 = 4 * keep_x1;
+        q.n_out_extra = n_extra;
+        for (int e = 0; e < n_extra; ++e) q.out_extra[e] = h_extra[e];
         SR_DO(run_conv(n->conv_last, q, s));
     }
 #undef SR_DO
     return K4_OK;
+}
+
+extern "C" int k4_srnet_forward_roi(const k4_srnet* n, const float* d_x, const float* d_cond, int32_t h, int32_t w,
+                                    int32_t keep_y0, int32_t keep_y1, int32_t keep_x0, int32_t keep_x1,
+                                    float* d_out, int64_t out_plane_stride, int64_t out_row_stride,
+                                    void* d_ws, size_t ws_bytes, k4_stream_t stream) {
+    return srnet_forward_roi_impl(n, d_x, d_cond, h, w, keep_y0, keep_y1, keep_x0, keep_x1, d_out, out_plane_stride,
+                                  out_row_stride, 0, nullptr, d_ws, ws_bytes, stream);
+}
+
+extern "C" int k4_srnet_forward_roi_peers(const k4_srnet* n, const float* d_x, const float* d_cond, int32_t h, int32_t w,
+                                          int32_t keep_y0, int32_t keep_y1, int32_t keep_x0, int32_t keep_x1,
+                                          float* d_out, int64_t out_plane_stride, int64_t out_row_stride,
+                                          int32_t n_extra, float* const* h_extra,
+                                          void* d_ws, size_t ws_bytes, k4_stream_t stream) {
+    return srnet_forward_roi_impl(n, d_x, d_cond, h, w, keep_y0, keep_y1, keep_x0, keep_x1, d_out, out_plane_stride,
+                                  out_row_stride, n_extra, h_extra, d_ws, ws_bytes, stream);
 }
 
 extern "C" int k4_srnet_forward(const k4_srnet* n, const float* d_x, const float* d_cond, int32_t h, int32_t w,

@@ -9,6 +9,7 @@ K4_OK = 0
 K4_KIND_DVGO, K4_KIND_DMPIGO, K4_KIND_DCVGO = 0, 1, 2
 K4_MLP_FP32, K4_MLP_F16, K4_MLP_F16X3, K4_MLP_TCGEN05, K4_MLP_TCGEN05_WS = 0, 1, 2, 3, 4
 K4_MAX_MLP_LAYERS = 8
+K4_MAX_PEERS = 8
 MLP_MODES = {'fp32': K4_MLP_FP32, 'f16': K4_MLP_F16, 'f16x3': K4_MLP_F16X3, 'tcgen05': K4_MLP_TCGEN05,
              'tc': K4_MLP_TCGEN05, 'ws': K4_MLP_TCGEN05_WS}
 
@@ -44,6 +45,13 @@ class RenderOut(C.Structure):
     ]
 
 
+class FrameDst(C.Structure):
+    _fields_ = [
+        ('n_dst', C.c_int32), ('rank', C.c_int32), ('world', C.c_int32), ('frame_w', C.c_int32),
+        ('n_full', C.c_int64), ('d_frame', C.c_void_p * K4_MAX_PEERS),
+    ]
+
+
 class SrnetDesc(C.Structure):
     _fields_ = [
         ('n_in_colors', C.c_int32), ('scale', C.c_int32), ('num_feat', C.c_int32), ('num_block', C.c_int32),
@@ -65,6 +73,13 @@ EXPORTS = {
     'k4_render_workspace_bytes': (C.c_size_t, [C.c_void_p, C.c_int64]),
     'k4_render_rays': (C.c_int, [C.c_void_p, C.POINTER(RenderArgs), C.c_void_p, C.c_void_p, C.c_void_p,
                                  C.c_int64, C.POINTER(RenderOut), C.c_void_p, C.c_size_t, C.c_void_p]),
+    'k4_render_rays_frames': (C.c_int, [C.c_void_p, C.POINTER(RenderArgs), C.c_void_p, C.c_void_p, C.c_void_p,
+                                        C.c_int64, C.POINTER(FrameDst), C.POINTER(RenderOut), C.c_void_p, C.c_size_t, C.c_void_p]),
+    'k4_peer_alloc': (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p)]),
+    'k4_peer_free': (C.c_int, [C.c_void_p]),
+    'k4_peer_export': (C.c_int, [C.c_void_p, C.c_char_p]),
+    'k4_peer_open': (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
+    'k4_peer_close': (C.c_int, [C.c_void_p]),
     'k4_srnet_create': (C.c_int, [C.POINTER(SrnetDesc), C.c_void_p, C.POINTER(C.c_void_p)]),
     'k4_srnet_destroy': (C.c_int, [C.c_void_p]),
     'k4_srnet_workspace_bytes': (C.c_size_t, [C.c_void_p, C.c_int32, C.c_int32]),
@@ -72,6 +87,9 @@ EXPORTS = {
                                    C.c_size_t, C.c_void_p]),
     'k4_srnet_forward_roi': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                        C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_size_t, C.c_void_p]),
+    'k4_srnet_forward_roi_peers': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                             C.c_int32, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.POINTER(C.c_void_p),
+                                             C.c_void_p, C.c_size_t, C.c_void_p]),
     'k4_op_infer_t_minmax': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     'k4_op_infer_n_samples': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_int64, C.c_void_p, C.c_void_p]),
     'k4_op_infer_ray_start_dir': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -183,7 +183,10 @@ class FusedRenderMixin:
                     debug=False, out=None):
         """Run the fused kernel.  Returns dict(rgb_marched, alphainv_last[, depth][, ray_stats, t_minmax, counters]).
         ``out``: optional dict of caller-owned contiguous fp32 CUDA tensors ``rgb_marched [N,3]``, ``alphainv_last [N]``
-        (and ``depth [N]``) the kernel writes into -- e.g. views of a packed communication buffer (k4nerf.dist)."""
+        (and ``depth [N]``) the kernel writes into -- e.g. views of a packed communication buffer (k4nerf.dist) -- or a
+        :class:`k4nerf.dist.FrameTarget`: the rays are one rank's rows of a block-cyclic multi-GPU frame and every ray is
+        stored straight into every rank's image-order frame (k4_render_rays_frames); the returned dict then holds only
+        the debug outputs."""
         assert rays_o.dim() == 2 and rays_o.shape[-1] == 3, 'Only suuport point queries in [N, 3] format'
         require_cuda(rays_o, rays_d, viewdirs)
         h = self._get_scene()
@@ -193,7 +196,12 @@ class FusedRenderMixin:
         viewdirs = viewdirs.to(torch.float32).contiguous()
         N = rays_o.shape[0]
         want_depth = bool(render_kwargs.get('render_depth', False))
-        if out is not None:
+        frames = getattr(out, 'frame_dst', None)
+        if frames is not None:
+            if N % int(frames.frame_w) != 0:
+                raise ValueError('render_rays(out=FrameTarget): the rays must be whole rows of the frame')
+            rgb = alphainv = depth = None
+        elif out is not None:
             rgb, alphainv, depth = out['rgb_marched'], out['alphainv_last'], (out.get('depth') if want_depth else None)
             for t, shp in ((rgb, (N, 3)), (alphainv, (N,)), (depth, (N,))):
                 if t is not None and not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and tuple(t.shape) == shp):
@@ -215,12 +223,15 @@ class FusedRenderMixin:
         keep = []
         self._extra_render_args(a, render_kwargs, dev, keep)
         o = _lib.RenderOut()
-        o.d_rgb_marched = rgb.data_ptr()
-        o.d_alphainv_last = alphainv.data_ptr()
-        o.d_depth = depth.data_ptr() if depth is not None else None
-        ret = {'rgb_marched': rgb, 'alphainv_last': alphainv}
-        if depth is not None:
-            ret['depth'] = depth
+        if frames is None:
+            o.d_rgb_marched = rgb.data_ptr()
+            o.d_alphainv_last = alphainv.data_ptr()
+            o.d_depth = depth.data_ptr() if depth is not None else None
+            ret = {'rgb_marched': rgb, 'alphainv_last': alphainv}
+            if depth is not None:
+                ret['depth'] = depth
+        else:
+            ret = {}
         if debug:
             ret['ray_stats'] = torch.zeros((N, 4), device=dev, dtype=torch.int32)
             ret['t_minmax'] = torch.zeros((N, 2), device=dev, dtype=torch.float32)
@@ -237,9 +248,14 @@ class FusedRenderMixin:
             object.__setattr__(self, '_k4_ws', ws)
         with torch.cuda.device(dev):
             stream = torch.cuda.current_stream(dev).cuda_stream
-            _lib.check(_lib.lib.k4_render_rays(h.ptr, C.byref(a), rays_o.data_ptr(), rays_d.data_ptr(),
-                                               viewdirs.data_ptr(), N, C.byref(o), ws.data_ptr(),
-                                               ws.numel(), C.c_void_p(stream)), 'k4_render_rays')
+            if frames is not None:
+                _lib.check(_lib.lib.k4_render_rays_frames(h.ptr, C.byref(a), rays_o.data_ptr(), rays_d.data_ptr(),
+                                                          viewdirs.data_ptr(), N, C.byref(frames), C.byref(o), ws.data_ptr(),
+                                                          ws.numel(), C.c_void_p(stream)), 'k4_render_rays_frames')
+            else:
+                _lib.check(_lib.lib.k4_render_rays(h.ptr, C.byref(a), rays_o.data_ptr(), rays_d.data_ptr(),
+                                                   viewdirs.data_ptr(), N, C.byref(o), ws.data_ptr(),
+                                                   ws.numel(), C.c_void_p(stream)), 'k4_render_rays')
         return ret
 
     def forward(self, rays_o, rays_d, viewdirs, global_step=None, **render_kwargs):

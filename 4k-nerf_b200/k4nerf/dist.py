@@ -12,6 +12,9 @@ GPUs, so results are bit-identical to the single-GPU render of the same rows.
 Works with any ``torch.distributed`` backend (``nccl`` on GPUs; ``gloo`` in the CPU tests, where a
 stand-in render function is injected because the kernel itself needs a GPU).
 """
+import ctypes as C
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -100,12 +103,134 @@ def unpack_frame(gathered, H, W, world_size):
     return {'rgb_marched': rgb.reshape(H * W, 3), 'depth': depth.reshape(H * W), 'alphainv_last': ainv.reshape(H * W)}
 
 
+class _DevMem:
+    """A raw device allocation presented through ``__cuda_array_interface__`` (torch.as_tensor aliases it)."""
+
+    def __init__(self, ptr, numel):
+        self.__cuda_array_interface__ = {'shape': (int(numel),), 'typestr': '<f4', 'data': (int(ptr), False),
+                                         'version': 2, 'strides': None}
+
+
+class PeerBuffers:
+    """``count`` fp32 device buffers of ``numel`` elements on every rank of ``group`` (one node, one process per GPU),
+    each mapped into every other rank's address space: ``local[i]`` is this rank's buffer ``i`` as a tensor,
+    ``ptrs[i][r]`` the device pointer under which THIS process reaches rank ``r``'s buffer ``i`` (``ptrs[i][rank]`` is the
+    local one).  The kernels store results straight into the peers' buffers over NVLink (k4_render_rays_frames,
+    k4_srnet_forward_roi_peers) -- SURVEY.md section 8e's "writing bands directly into peer-mapped output buffers" --
+    and ``sync()`` orders the ranks: a one-element all-reduce enqueued behind the stores; once it has completed on a
+    rank's stream, every rank's launch -- and with it every store into this rank's buffer -- has completed.
+
+    The memory comes from the library (``k4_peer_alloc``: plain cudaMalloc, the caching allocator's blocks cannot be
+    exported one by one) and is shared with CUDA IPC handles sent through ``all_gather_object``.  ``create`` is
+    COLLECTIVE and returns ``None`` on every rank if any rank cannot allocate / export / map (not CUDA, ranks on
+    different nodes, more than 8 ranks, ``K4_PEER=0``): the callers then use the all-gather path."""
+
+    last_error = None          # why the last create() on this rank fell back (diagnostics)
+
+    def __init__(self):
+        self.local, self.ptrs, self._opened, self._owned = [], [], [], []
+
+    @classmethod
+    def create(cls, numel, device, group=None, count=2):
+        from . import _lib
+        device = torch.device(device)
+        if not dist.is_initialized() or device.type != 'cuda' or os.environ.get('K4_PEER', '1') == '0':
+            return None
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        if world < 2 or world > _lib.K4_MAX_PEERS:
+            return None
+        self = cls()
+        self.group, self.world, self.rank, self.device, self.numel = group, world, rank, device, int(numel)
+        ok, handles = 1, []
+        with torch.cuda.device(device):
+            try:
+                for _ in range(count):
+                    p = C.c_void_p()
+                    _lib.check(_lib.lib.k4_peer_alloc(C.c_size_t(4 * self.numel), C.byref(p)), 'k4_peer_alloc')
+                    self._owned.append(p.value)
+                    h = C.create_string_buffer(64)
+                    _lib.check(_lib.lib.k4_peer_export(C.c_void_p(p.value), h), 'k4_peer_export')
+                    handles.append(h.raw)
+            except Exception as e:
+                ok, cls.last_error = 0, 'alloc/export: ' + repr(e)
+            info = [None] * world
+            dist.all_gather_object(info, (ok, handles, os.uname().nodename), group=group)
+            ok = int(all(i[0] for i in info) and len({i[2] for i in info}) == 1)
+            if ok:
+                try:
+                    for i in range(count):
+                        row = []
+                        for r in range(world):
+                            if r == rank:
+                                row.append(self._owned[i])
+                                continue
+                            q = C.c_void_p()
+                            _lib.check(_lib.lib.k4_peer_open(info[r][1][i], C.byref(q)), 'k4_peer_open')
+                            self._opened.append(q.value)
+                            row.append(q.value)
+                        self.ptrs.append(row)
+                    self.local = [torch.as_tensor(_DevMem(p, self.numel), device=device) for p in self._owned]
+                    if any(t.data_ptr() != p or not t.is_cuda for t, p in zip(self.local, self._owned)):
+                        ok, cls.last_error = 0, 'torch.as_tensor copied the buffer instead of aliasing it'
+                except Exception as e:
+                    ok, cls.last_error = 0, 'open/alias: ' + repr(e)
+            elif cls.last_error is None:
+                cls.last_error = 'another rank failed or the ranks span nodes: ' + repr([(i[0], i[2]) for i in info])
+            t = torch.tensor([ok], device=device, dtype=torch.int32)
+            dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)
+            if int(t.item()) == 0:
+                self.close()
+                return None
+            self._flag = torch.zeros(1, device=device, dtype=torch.float32)
+        return self
+
+    def sync(self):
+        """Stream-ordered barrier of the group (no host wait): behind it, the stores every rank issued before ITS
+        ``sync()`` are complete."""
+        dist.all_reduce(self._flag, group=self.group)
+
+    def close(self):
+        from . import _lib
+        self.local = []
+        for p in self._opened:
+            _lib.lib.k4_peer_close(C.c_void_p(p))
+        for p in self._owned:
+            _lib.lib.k4_peer_free(C.c_void_p(p))
+        self._opened, self._owned, self.ptrs = [], [], []
+
+
+class FrameTarget:
+    """Where one rank's rows of a block-cyclic frame go: ``frame_dst`` is the filled ``k4_frame_dst`` for
+    ``render_rays(out=...)`` (every rank's image-order frame, the peers' reached through NVLink)."""
+
+    def __init__(self, ptrs, rank, world, W, n_full):
+        from . import _lib
+        d = _lib.FrameDst()
+        d.n_dst, d.rank, d.world, d.frame_w, d.n_full = len(ptrs), rank, world, W, n_full
+        for i, p in enumerate(ptrs):
+            d.d_frame[i] = p
+        self.frame_dst = d
+
+
+def frame_views(full, H, W, n_full):
+    """dict views of an image-order frame buffer ``[rgb 3 n_full | depth n_full | alphainv n_full]``."""
+    return {'rgb_marched': full[:3 * H * W].view(H * W, 3), 'depth': full[3 * n_full:3 * n_full + H * W],
+            'alphainv_last': full[4 * n_full:4 * n_full + H * W]}
+
+
 class CyclicFrame:
-    """Cached plan + buffers of one rank for block-cyclic frame rendering (H x W over `world` ranks): the
-    rank's row list on the device, its packed send buffer (pad zeroed once) with output views for the
-    marcher, and the gather buffer.  ``render(make_rays, render_fn)`` = rays of the rank's rows only
-    (``make_rays(rows) -> ro, rd, vd`` each [k*W,3]) -> fused march straight into the packed buffer ->
-    ONE all-gather -> image-order transpose."""
+    """Cached plan + buffers of one rank for block-cyclic frame rendering (H x W over `world` ranks).
+
+    ``render(make_rays, render_fn)`` = rays of the rank's rows only (``make_rays(rows) -> ro, rd, vd`` each [k*W,3]) ->
+    fused march with ``render_fn(ro, rd, vd, (k, W), out)`` -> exchange -> every rank holds the frame in image order.
+
+    Two exchanges.  PEER (default on the GPUs of one node): ``out`` is a :class:`FrameTarget` and the marcher stores
+    every ray straight into the image-order frame of every rank (NVLink P2P stores from inside the kernel, overlapped
+    with the march); a one-element all-reduce orders the ranks.  No band buffer, no all-gather, no transpose.  Two frame
+    buffers alternate, so a rank that is one frame ahead never overwrites the frame another rank is still reading.
+    GATHER (gloo / CPU tests, ``K4_PEER=0``, anything :class:`PeerBuffers` cannot map): ``out`` is a dict of views
+    of the rank's packed send buffer (pad zeroed once), then ONE all-gather and the image-order transpose into a frame
+    buffer allocated once."""
 
     def __init__(self, H, W, device, group=None):
         self.H, self.W, self.group = H, W, group
@@ -115,6 +240,12 @@ class CyclicFrame:
         self.k = int(self.rows.numel())
         self.n_band = self.k * W
         self.n_pad = cyclic_pad_rows(H, self.world) * W
+        self.n_full = self.world * self.n_pad
+        self.step = 0
+        self.peers = PeerBuffers.create(5 * self.n_full, device, group, count=2) if self.world > 1 else None
+        if self.peers is not None:
+            self.targets = [FrameTarget(self.peers.ptrs[i], self.rank, self.world, W, self.n_full) for i in range(2)]
+            return
         self.buf = torch.zeros(5 * self.n_pad, device=device, dtype=torch.float32)
         self.out = packed_band_views(self.buf, self.n_band, self.n_pad)
         self.gathered = torch.empty(self.world * 5 * self.n_pad, device=device, dtype=torch.float32) if self.world > 1 else self.buf
@@ -122,9 +253,23 @@ class CyclicFrame:
         # synchronises the device, and with NCCL's peer mappings in place it is slow)
         self.full = torch.empty(self.world * 5 * self.n_pad, device=device, dtype=torch.float32)
 
+    def target(self):
+        """``out=`` of this step's ``render_rays`` call: the peer frames of the step's parity, or the send-buffer views."""
+        return self.targets[self.step & 1] if self.peers is not None else self.out
+
+    def finish(self):
+        """Complete the step's exchange; returns the frame (views, valid until the step after the next one in peer
+        mode, until the next step in gather mode -- clone to keep one longer)."""
+        if self.peers is not None:
+            self.peers.sync()
+            full = self.peers.local[self.step & 1]
+            self.step += 1
+            return frame_views(full, self.H, self.W, self.n_full)
+        self.step += 1
+        return self.gather()
+
     def gather(self):
-        """All-gather + image-order transpose.  The returned tensors are views of this object's frame buffer: they hold
-        the frame until the next ``gather()`` (clone to keep one longer)."""
+        """(gather mode) all-gather + image-order transpose."""
         if self.world > 1:
             dist.all_gather_into_tensor(self.gathered, self.buf, group=self.group)
         return unpack_frame_cyclic(self.gathered, self.H, self.W, self.world, out=self.full)
@@ -132,8 +277,8 @@ class CyclicFrame:
     def render(self, make_rays, render_fn):
         if self.k > 0:
             ro, rd, vd = make_rays(self.rows)
-            render_fn(ro, rd, vd, (self.k, self.W), self.out)
-        return self.gather()
+            render_fn(ro, rd, vd, (self.k, self.W), self.target())
+        return self.finish()
 
 
 def render_frame_sharded(render_fn, rays_o, rays_d, viewdirs, H, W, group=None, gather=True, layout='cyclic'):
@@ -281,7 +426,8 @@ def sr_assign(units, world_size):
     return [sorted(m) for m in mine]
 
 
-def sr_decode_sharded(net_fn, img, cond, tile_size, tile_pad=10, scale=4, halo=80, group=None, net_units_fn=None):
+def sr_decode_sharded(net_fn, img, cond, tile_size, tile_pad=10, scale=4, halo=80, group=None, net_units_fn=None,
+                      peers=None):
     """x`scale` decode of ``img [1,C,H,W]`` / ``cond [1,H,W]`` (full frame on every rank) with the units
     of :func:`sr_units` dealt round-robin over the ranks and ONE all-gather of the packed output
     blocks.  ``net_fn(img_crop, cond_crop[1,1,h,w]) -> [1,C,scale*h,scale*w]`` is the decoder
@@ -289,7 +435,9 @@ def sr_decode_sharded(net_fn, img, cond, tile_size, tile_pad=10, scale=4, halo=8
     (``SFTNet.run_units``), when given, writes every unit's kept block straight into the packed send buffer, lets every
     layer skip the rows outside the kept block's remaining receptive field and overlaps a rank's units on two
     streams.  Every rank returns the full
-    ``[1,C,scale*H,scale*W]`` frame."""
+    ``[1,C,scale*H,scale*W]`` frame.  ``peers`` (a :class:`PeerBuffers` of ``C*scale*H*scale*W`` elements, with
+    ``net_units_fn``): no packed buffer, no all-gather, no assembly -- every unit's kept block is stored by the
+    decoder's last kernel into the frame of EVERY rank (its own and, over NVLink, the peers'), then ``peers.sync()``."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     _, C, H, W = img.shape
@@ -297,6 +445,24 @@ def sr_decode_sharded(net_fn, img, cond, tile_size, tile_pad=10, scale=4, halo=8
     units = sr_units(H, W, tile_size, tile_pad, world, halo)
     size = lambda u: C * (u['dst'][1] - u['dst'][0]) * (u['dst'][3] - u['dst'][2]) * s * s
     assign = sr_assign(units, world)
+    if peers is not None and net_units_fn is not None and world > 1:
+        par = peers.__dict__.setdefault('_step', 0) & 1
+        peers._step += 1
+        output = peers.local[par].view(1, C, H * s, W * s)
+        cond4 = cond.unsqueeze(0)
+        jobs = []
+        for u in (units[i] for i in assign[rank]):
+            sa, sb, xa, xb = u['src']
+            ky, kx = u['keep']
+            y0, y1, x0, x1 = u['dst']
+            blk = output[0, :, y0 * s:y1 * s, x0 * s:x1 * s]
+            off = 4 * (blk.storage_offset() - output.storage_offset())          # same window in every rank's frame
+            extra = [peers.ptrs[par][r] + off for r in range(world) if r != rank]
+            jobs.append((img[:, :, sa:sb, xa:xb], cond4[:, :, sa:sb, xa:xb], (ky, ky + y1 - y0, kx, kx + x1 - x0), blk, extra))
+        if jobs:
+            net_units_fn(jobs)
+        peers.sync()
+        return output
     per_rank = [sum(size(units[i]) for i in assign[r]) for r in range(world)]
     n_pad = max(per_rank) if per_rank else 0
     buf = torch.empty(n_pad, device=img.device, dtype=img.dtype)

@@ -128,11 +128,13 @@ class SFTNet(nn.Module):
         return ws
 
     @torch.no_grad()
-    def forward_roi(self, x, cond, keep, out, ws_slot=0):
+    def forward_roi(self, x, cond, keep, out, ws_slot=0, extra=None):
         """The x4 pixels of LR block ``keep = (y0, y1, x0, x1)`` of tile ``x [1,3,h,w]`` / ``cond [1,1,h,w]`` written
         into ``out``: a ``[3, 4(y1-y0), 4(x1-x0)]`` fp32 CUDA view with unit stride along x (typically a window of the
         frame).  Same values as ``forward(x, cond)[0, :, 4y0:4y1, 4x0:4x1]``; every layer computes only the rows inside the
-        remaining receptive field of the kept rows (k4_srnet_forward_roi).  Runs on the current stream."""
+        remaining receptive field of the kept rows (k4_srnet_forward_roi).  Runs on the current stream.  ``extra``: device
+        pointers (ints) of the same window in other ranks' peer-mapped frames -- the last convolution stores the block there
+        too (k4_srnet_forward_roi_peers)."""
         require_cuda(x, cond, out)
         assert x.dim() == 4 and x.shape[0] == 1 and x.shape[1] == 3 and cond.shape[1] == 1, 'batch 1, 3+1 channels'
         h, w = int(x.shape[2]), int(x.shape[3])
@@ -147,14 +149,21 @@ class SFTNet(nn.Module):
         ws = self._workspace(nbytes, dev, ws_slot)
         with torch.cuda.device(dev):
             stream = torch.cuda.current_stream(dev).cuda_stream
-            _lib.check(_lib.lib.k4_srnet_forward_roi(net.ptr, x.data_ptr(), cond.data_ptr(), h, w, y0, y1, x0, x1,
-                                                     out.data_ptr(), int(out.stride(0)), int(out.stride(1)),
-                                                     ws.data_ptr(), ws.numel(), C.c_void_p(stream)), 'k4_srnet_forward_roi')
+            if extra:
+                arr = (C.c_void_p * len(extra))(*[int(e) for e in extra])
+                _lib.check(_lib.lib.k4_srnet_forward_roi_peers(net.ptr, x.data_ptr(), cond.data_ptr(), h, w, y0, y1, x0, x1,
+                                                               out.data_ptr(), int(out.stride(0)), int(out.stride(1)),
+                                                               len(extra), arr, ws.data_ptr(), ws.numel(),
+                                                               C.c_void_p(stream)), 'k4_srnet_forward_roi_peers')
+            else:
+                _lib.check(_lib.lib.k4_srnet_forward_roi(net.ptr, x.data_ptr(), cond.data_ptr(), h, w, y0, y1, x0, x1,
+                                                         out.data_ptr(), int(out.stride(0)), int(out.stride(1)),
+                                                         ws.data_ptr(), ws.numel(), C.c_void_p(stream)), 'k4_srnet_forward_roi')
         return out
 
     @torch.no_grad()
     def run_units(self, jobs, streams=2):
-        """``forward_roi`` for a list of independent jobs ``(x_crop, cond_crop, keep, out_view)`` dealt (largest first) to
+        """``forward_roi`` for a list of independent jobs ``(x_crop, cond_crop, keep, out_view[, extra])`` dealt (largest first) to
         ``streams`` CUDA streams with a workspace each; returns when the current stream has been made to wait for all of
         them.  Independent units overlap each other's launch / fill / drain phases (~120 kernels per unit)."""
         if not jobs:
@@ -171,7 +180,8 @@ class SFTNet(nn.Module):
         load = [0] * n_streams
         used = set()
         for i in order:
-            x, c, keep, out = jobs[i]
+            x, c, keep, out = jobs[i][:4]
+            extra = jobs[i][4] if len(jobs[i]) > 4 else None
             k = min(range(n_streams), key=lambda j: load[j])
             load[k] += x.shape[2] * x.shape[3]
             st = pool[k]
@@ -180,7 +190,7 @@ class SFTNet(nn.Module):
                     st.wait_event(ready)
                 used.add(k)
                 xt, ct = x.contiguous(), c.contiguous()
-                self.forward_roi(xt, ct, keep, out, ws_slot=k)
+                self.forward_roi(xt, ct, keep, out, ws_slot=k, extra=extra)
                 if k > 0:
                     xt.record_stream(st); ct.record_stream(st)
         for k in sorted(used - {0}):
@@ -239,12 +249,23 @@ class SFTNet(nn.Module):
 
     def tile_process_sharded(self, img, cond, tile_size, tile_pad=10, group=None):
         """tile_process across the ranks of ``group``: reference tiles (split into
-        row parts with a recomputed halo when ranks outnumber tiles) dealt round-robin, one all-gather;
-        every rank returns the same full frame as single-GPU ``tile_process`` (device resident)."""
+        row parts with a recomputed halo when ranks outnumber tiles) dealt to the ranks; every rank returns the same
+        full frame as single-GPU ``tile_process`` (device resident).  On the GPUs of one node every unit's last
+        convolution stores its kept block straight into every rank's frame (peer-mapped, :class:`k4nerf.dist.PeerBuffers`;
+        two frames alternate, the returned one is valid until the call after the next one); otherwise one all-gather of
+        the packed blocks + assembly."""
         from . import dist as kdist
+        batch, channel, height, width = img.shape
+        peers = None
+        if img.is_cuda and kdist.dist.is_initialized():
+            cache = self.__dict__.setdefault('_k4_peer_frames', {})
+            key = (channel, height, width, img.device, id(group))
+            if key not in cache:       # collective: every rank decodes the same frame shape
+                cache[key] = kdist.PeerBuffers.create(channel * height * width * self.scale ** 2, img.device, group, count=2)
+            peers = cache[key]
         return kdist.sr_decode_sharded(lambda x, c: self(x, c), img, cond, tile_size, tile_pad, self.scale,
                                        self.receptive_halo(), group,
-                                       net_units_fn=lambda jobs: self.run_units(jobs, streams=2))
+                                       net_units_fn=lambda jobs: self.run_units(jobs, streams=2), peers=peers)
 
     def load_network(self, load_path, device, strict=True, param_key='params_ema'):
         """lib/sr_esrnet.py:529-554 (keys may carry a 'module.' prefix; mismatching sizes are skipped

@@ -245,7 +245,9 @@ def workload_config(args, n_gpus):
                     'stepsize 0.5) marched at 4032x3024 rays/step',
         'regime': args.regime, 'rays_per_step': H4K * W4K, 'grid': [GRID_RES] * 3, 'k0_dim': 12,
         'mlp': [39, 128, 128, 3],
-        'parallelism': f'8-row blocks dealt round-robin over {n_gpus} rank(s)' + (' + nccl all_gather' if n_gpus > 1 else ''),
+        'parallelism': f'8-row blocks dealt round-robin over {n_gpus} rank(s)' + (
+            '; exchange: in-kernel NVLink stores into every rank\'s peer-mapped frame + 1-element all-reduce as barrier '
+            '(nccl all_gather + transpose when peer mapping is unavailable; see "exchange")' if n_gpus > 1 else ''),
         'l2_policy': 'inputs larger than L2 (439 MB rays + 213 MB grids per step), pose changes every step',
     }
 
@@ -289,7 +291,7 @@ def main():
     # (8-row blocks dealt round-robin over the ranks: every rank gets the same mix of long and short rays;
     # only the rank's rows are generated -- k4_make_rays_rows)
     H, W = H4K, W4K
-    frame = kdist.CyclicFrame(H, W, dev)              # row list, packed send buffer (marcher output views), gather buffer
+    frame = kdist.CyclicFrame(H, W, dev)              # row list + peer-mapped frames (or packed send / gather buffers)
     n_rows = frame.k
     r0, r1 = 0, n_rows                                   # local image = this rank's rows, in order
     from oracle import scenes as _scenes
@@ -302,11 +304,13 @@ def main():
     n_band = n_rows * W
 
     def step(i):
-        """One step = one fused launch over this rank's rows (written straight into the packed buffer) and, for
-        N > 1, ONE all-gather + the image-order transpose: every rank ends the step holding the whole frame."""
+        """One step = one fused launch over this rank's rows and, for N > 1, the exchange that leaves the whole frame,
+        in image order, on every rank: NVLink stores into every rank's frame from inside the kernel + a one-element
+        all-reduce as the barrier (k4nerf.dist.CyclicFrame, peer mode), or -- K4_PEER=0 / no peer mapping -- the packed
+        band buffer, ONE all-gather and the image-order transpose."""
         ro, rd, vd = bands[i % len(bands)]
-        model.render_rays(ro, rd, vd, kw, image_hw=(r1 - r0, W), mlp_mode=mode, out=frame.out)
-        return frame.gather() if world > 1 else frame.out
+        model.render_rays(ro, rd, vd, kw, image_hw=(r1 - r0, W), mlp_mode=mode, out=frame.target())
+        return frame.finish() if world > 1 else frame.out
 
     def barrier():
         if world > 1:
@@ -330,14 +334,16 @@ def main():
         step(i)
     gather_ms = None
     if world > 1:
-        # NCCL sets up its channels lazily: a few more gathers of the frame before the clock starts, and their time on its own
+        # NCCL sets up its channels lazily: a few more exchanges before the clock starts, and their time on its own
+        # (peer mode: the barrier only -- the data moved inside the kernel; gather mode: all-gather + transpose)
+        exch = frame.peers.sync if frame.peers is not None else frame.gather
         for _ in range(5):
-            frame.gather()
+            exch()
         barrier()
         g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         g0.record()
         for _ in range(5):
-            frame.gather()
+            exch()
         g1.record()
         torch.cuda.synchronize()
         gather_ms = g0.elapsed_time(g1) / 5
@@ -355,10 +361,10 @@ def main():
     for i in range(args.steps):
         ro, rd, vd = bands[i % len(bands)]
         k_events[i][0].record()
-        model.render_rays(ro, rd, vd, kw, image_hw=(r1 - r0, W), mlp_mode=mode, out=frame.out)
+        model.render_rays(ro, rd, vd, kw, image_hw=(r1 - r0, W), mlp_mode=mode, out=frame.target())
         k_events[i][1].record()
         if world > 1:
-            full = frame.gather()                        # all-gather + transpose into image order
+            full = frame.finish()                        # every rank now holds the frame in image order
     e1.record()
     barrier()
     t_wall1 = time.time()
@@ -385,6 +391,15 @@ def main():
 
     def e2e_step(i):
         ro, rd, vd = [x.to(dev, non_blocking=True) for x in hb[i % len(hb)]]
+        if world > 1 and frame.peers is not None:
+            # peer mode: the kernel stores into every rank's frame; each rank copies ITS 1/world share of the frame back
+            model.render_rays(ro, rd, vd, kw, image_hw=(r1 - r0, W), mlp_mode=mode, out=frame.target())
+            par = frame.step & 1
+            frame.finish()
+            share = (5 * frame.n_full) // world
+            n = min(share, h_out.numel())
+            h_out[:n].copy_(frame.peers.local[par][rank * share:rank * share + n], non_blocking=True)
+            return
         model.render_rays(ro, rd, vd, kw, image_hw=(r1 - r0, W), mlp_mode=mode, out=e2e_out)
         if world > 1:
             frame.buf[:3 * n_band].copy_(e2e_buf[:3 * n_band])
@@ -444,7 +459,8 @@ def main():
                       'ws': 'f32 geometry/interpolation/compositing; rgbnet f16 operands, f32 accumulate (tcgen05)'}[mode],
             'data': 'synthetic', 'config': workload_config(args, world), 'mlp_mode': mode,
             'e2e': e2e, 'gpu_launches': args.steps, 'clocks': clocks,
-            **({'gather_unpack_ms_rank0': gather_ms} if gather_ms is not None else {}),
+            **({'exchange': 'peer_stores' if frame.peers is not None else 'all_gather',
+                'exchange_alone_ms_rank0': gather_ms} if gather_ms is not None else {}),
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
                          'traffic': traffic, 'peak_source': peak_src,
                          'kernel': kernel_name,

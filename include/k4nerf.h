@@ -58,6 +58,7 @@ enum { K4_MLP_FP32 = 0,                    /* fp32 FFMA, sequential accumulation
        K4_MLP_TCGEN05_WS = 4 };            /* same, MLP in its own warpgroup (warp-specialised)  */
 
 #define K4_MAX_MLP_LAYERS 8
+#define K4_MAX_PEERS 8            /* GPUs of one NVLink / NVSwitch node */
 
 /*
  * Scene description = the tensors of a reference checkpoint's `model_state_dict` plus the derived
@@ -161,6 +162,40 @@ K4_API int k4_render_rays(const k4_scene* scene, const k4_render_args* args,
                    void* d_workspace, size_t workspace_bytes, k4_stream_t stream);
 
 /*
+ * Multi-GPU frames (the reference has no multi-GPU path -- run_sr.py:99-128 renders every frame on
+ * one device): the same fused launch for ONE RANK'S ROWS of a frame that is sharded in 8-row blocks dealt round-robin
+ * over `world` ranks, with the exchange fused into the kernel: every ray's results are stored straight into the
+ * image-order frame of EVERY rank -- d_frame[i] are the local frame and the peers' frames mapped with k4_peer_open
+ * (NVLink P2P stores) -- instead of a local band buffer followed by an all-gather and a transpose.  The rays passed are
+ * the rank's rows in order (k4_make_rays_rows), n_rays = rows * frame_w; local row r is image row
+ * ((r / 8) * world + rank) * 8 + r % 8.  A frame is 5 * n_full floats: rgb [n_full,3] | depth [n_full] | alphainv
+ * [n_full], n_full >= the padded image (world * ceil(ceil(H/8) / world) * 8 rows).  `out` may be NULL or carry the
+ * optional parity outputs (d_ray_stats / d_t_minmax / d_counters, local ray order).  The stores are complete when the
+ * launch has completed on this rank's stream; the caller orders the ranks (any barrier that follows it in stream order).
+ */
+typedef struct k4_frame_dst {
+    int32_t n_dst;                /* frames to write: 1 .. K4_MAX_PEERS                                  */
+    int32_t rank, world;          /* block-cyclic position of the rows of this call                      */
+    int32_t frame_w;              /* W                                                                   */
+    int64_t n_full;               /* rays per (padded) frame                                             */
+    float* d_frame[K4_MAX_PEERS];
+} k4_frame_dst;
+K4_API int k4_render_rays_frames(const k4_scene* scene, const k4_render_args* args,
+                   const float* d_rays_o, const float* d_rays_d, const float* d_viewdirs,
+                   int64_t n_rays, const k4_frame_dst* dst, const k4_render_out* out,
+                   void* d_workspace, size_t workspace_bytes, k4_stream_t stream);
+
+/* Device memory other processes of the node can map (one process per GPU): k4_peer_alloc = cudaMalloc + zero fill
+ * (pool / async allocations cannot be exported), k4_peer_export fills the 64-byte CUDA IPC handle to send to the other
+ * ranks (any transport: torch.distributed.all_gather_object), k4_peer_open maps another PROCESS's allocation into the
+ * current device's address space with peer access enabled, k4_peer_close unmaps it. */
+K4_API int k4_peer_alloc(size_t bytes, void** d_ptr);
+K4_API int k4_peer_free(void* d_ptr);
+K4_API int k4_peer_export(void* d_ptr, unsigned char handle[64]);
+K4_API int k4_peer_open(const unsigned char handle[64], void** d_ptr);
+K4_API int k4_peer_close(void* d_ptr);
+
+/*
  * Replaces: get_rays_of_a_view (lib/dvgo.py:516-582) feeding the chunk loop of render_viewpoints
  * (run_sr.py:99-128): pixel-centre rays of an HxW pinhole view generated on the device.
  * h_K: 9 floats row major, h_c2w: 12 floats (3x4) row major, both HOST pointers.
@@ -219,6 +254,16 @@ K4_API int k4_srnet_forward_roi(const k4_srnet* net, const float* d_x, const flo
                                 int32_t keep_y0, int32_t keep_y1, int32_t keep_x0, int32_t keep_x1,
                                 float* d_out, int64_t out_plane_stride, int64_t out_row_stride,
                                 void* d_workspace, size_t workspace_bytes, k4_stream_t stream);
+
+/* k4_srnet_forward_roi whose last convolution stores the kept block into n_extra MORE frames as well (h_extra: HOST array
+ * of device pointers with d_out's meaning and strides -- the same window of the other ranks' frames, mapped with
+ * k4_peer_open): the multi-GPU decoder's exchange fused into the kernel that produces the pixels, instead of an
+ * all-gather of packed blocks and an assembly pass.  n_extra <= K4_MAX_PEERS - 1. */
+K4_API int k4_srnet_forward_roi_peers(const k4_srnet* net, const float* d_x, const float* d_cond, int32_t h, int32_t w,
+                                      int32_t keep_y0, int32_t keep_y1, int32_t keep_x0, int32_t keep_x1,
+                                      float* d_out, int64_t out_plane_stride, int64_t out_row_stride,
+                                      int32_t n_extra, float* const* h_extra,
+                                      void* d_workspace, size_t workspace_bytes, k4_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Op-level surface: the 13 functions of the reference extension `render_utils_cuda`

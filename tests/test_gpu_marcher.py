@@ -301,3 +301,37 @@ def test_empty_space_skipping_preserves_results(cuda_device, kind, regime, monke
             else:
                 assert (a['rgb_marched'] - b['rgb_marched']).abs().max().item() < 3e-5
     check_geometry(outs[(True, 'ws', (96, 128))], ref, stats, st, ro.shape[0])
+
+
+@pytest.mark.parametrize('mode', ['f16x3', 'ws', 'tc', 'fp32'])
+def test_render_rays_frames_assembles_the_block_cyclic_frame(cuda_device, mode):
+    """k4_render_rays_frames: every rank's rows (8-row blocks dealt round-robin) stored by the kernel straight into the
+    image-order frames -- here three 'ranks' one after the other on one GPU, two destination frames each (on a multi-GPU
+    node the second one is a peer's frame reached over NVLink).  The assembled frame equals the one-launch frame."""
+    from k4nerf import dist as kdist
+    st = make_state('cfgA', res=48, regime='fog')
+    H, W, world = 50, 72, 3                       # 7 blocks: ranks get 3 / 2 / 2 blocks, the last block is 2 rows
+    rays, kw = rays_for(st, H, W)
+    kw = dict(kw); kw['render_depth'] = True
+    m = model_from_state(st, cuda_device)
+    ro, rd, vd = [t.to(cuda_device) for t in rays]
+    ref = m.render_rays(ro, rd, vd, kw, image_hw=(H, W), mlp_mode=mode)
+    n_full = world * kdist.cyclic_pad_rows(H, world) * W
+    frames = [torch.full((5 * n_full,), -3.0, device=cuda_device) for _ in range(2)]
+    for rank in range(world):
+        rows = kdist.cyclic_rows(H, rank, world).to(cuda_device)
+        sel = lambda t: t.view(H, W, 3)[rows].reshape(-1, 3).contiguous()
+        tgt = kdist.FrameTarget([f.data_ptr() for f in frames], rank, world, W, n_full)
+        hw = (rows.numel(), W) if rank != 1 else None            # rank 1: the linear (no image tiles) ray order
+        m.render_rays(sel(ro), sel(rd), sel(vd), kw, image_hw=hw, mlp_mode=mode, out=tgt)
+    torch.cuda.synchronize()
+    assert torch.equal(frames[0], frames[1])
+    got = kdist.frame_views(frames[0], H, W, n_full)
+    exact = mode in ('f16x3', 'fp32')              # the tcgen05 kernels composite with shared-memory atomics: order-dependent rounding
+    for k in ('rgb_marched', 'depth', 'alphainv_last'):
+        if exact:
+            assert torch.equal(got[k], ref[k]), k
+        else:
+            assert torch.allclose(got[k], ref[k], rtol=0, atol=2e-5), (k, (got[k] - ref[k]).abs().max().item())
+    # nothing outside the image rows was touched
+    assert bool((frames[0][3 * H * W:3 * n_full] == -3.0).all()) and bool((frames[0][3 * n_full + H * W:4 * n_full] == -3.0).all())

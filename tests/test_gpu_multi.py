@@ -1,0 +1,39 @@
+"""Two GPUs of one node (skipped on a single-GPU box): the sharded full frame -- marcher rows stored from inside the kernel
+into every rank's peer-mapped frame, decoder blocks stored by the last convolution into every rank's 4K frame -- equals
+the single-GPU frame bit for bit on every rank, with both exchanges (peer stores, all-gather)."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(env_extra):
+    env = dict(os.environ)
+    env.update(env_extra)
+    cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2', '--master-addr', '127.0.0.1',
+           '--master-port', '29581', os.path.join(ROOT, 'tools', 'frame_sharded_check.py'), '--quick']
+    out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = [l for l in out.stdout.splitlines() if l.startswith('{')][-1]
+    return json.loads(line)
+
+
+@pytest.mark.skipif(not torch.cuda.is_available() or torch.cuda.device_count() < 2, reason='needs 2 GPUs')
+@pytest.mark.parametrize('peer', ['1', '0'])
+def test_sharded_frame_is_bit_identical_on_two_gpus(peer):
+    res = _run({'K4_PEER': peer})
+    assert res['n_gpus'] == 2
+    for regime in ('shell', 'fog'):
+        assert res[regime]['sr_identical_all_ranks'] and res[regime]['lr_identical_all_ranks'], res
+    if peer == '0':
+        assert res['exchange'] == {'marcher': 'all_gather', 'decoder': 'all_gather'}
+    else:
+        # peer mapping must work on the GPUs of one NVLink node; a silent fall back to the all-gather would hide a regression
+        assert res['exchange'] == {'marcher': 'peer_stores', 'decoder': 'peer_stores'}, res['exchange']

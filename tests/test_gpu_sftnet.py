@@ -246,3 +246,27 @@ def test_fused_sft_epilogues_match_the_separate_sft_passes(net, cuda_device, mon
     pa, pb, pab = pipeline.psnr(a.cpu(), ref), pipeline.psnr(b.cpu(), ref), pipeline.psnr(a.cpu(), b.cpu())
     print('fused vs fp32', pa, 'unfused vs fp32', pb, 'fused vs unfused', pab)
     assert pa >= 60.0 and pb >= 60.0 and pab >= 66.0
+
+
+def test_forward_roi_extra_destinations_receive_the_same_block(net, cuda_device):
+    """k4_srnet_forward_roi_peers: the last convolution stores the kept block into further frames too (on a multi-GPU
+    node: the other ranks' peer-mapped frames; here: two more local buffers), same window, same strides."""
+    g = torch.Generator().manual_seed(43)
+    h, w = 96, 52
+    x = (torch.rand(1, 3, h, w, generator=g) * 1.2 - 0.1).to(cuda_device)
+    c = torch.rand(1, 1, h, w, generator=g).to(cuda_device)
+    full = net(x, c)
+    frames = [torch.full((3, 4 * h, 4 * w), -7.0, device=cuda_device) for _ in range(3)]
+    for keep in ((0, h, 0, w), (10, 61, 3, 40)):
+        y0, y1, x0, x1 = keep
+        for f in frames:
+            f.fill_(-7.0)
+        win = lambda f: f[:, 4 * y0:4 * y1, 4 * x0:4 * x1]
+        dst = win(frames[0])
+        off = 4 * dst.storage_offset()
+        net.forward_roi(x, c, keep, dst, extra=[f.data_ptr() + off for f in frames[1:]])
+        for f in frames:
+            assert torch.equal(win(f), full[0, :, 4 * y0:4 * y1, 4 * x0:4 * x1]), keep
+            chk = f.clone()
+            win(chk).fill_(-7.0)
+            assert bool((chk == -7.0).all()), ('wrote outside the destination window', keep)

@@ -1,5 +1,6 @@
 """torchrun check (N GPUs of one node): the sharded full-frame driver returns, on every rank, exactly
-the frame the single-GPU driver returns.  torchrun --nproc-per-node N tools/frame_sharded_check.py"""
+the frame the single-GPU driver returns.  torchrun --nproc-per-node N tools/frame_sharded_check.py [--quick]
+(K4_PEER=0 in the environment: the all-gather exchange instead of in-kernel peer stores; --quick: no timing loops)"""
 import json
 import os
 import sys
@@ -14,6 +15,7 @@ sys.path.insert(0, os.path.join(ROOT, 'tests'))
 
 import k4nerf  # noqa: E402
 from k4nerf import render as krender  # noqa: E402
+from k4nerf import dist as krender_dist  # noqa: E402
 from helpers import make_state, model_from_state  # noqa: E402
 from oracle import scenes, sftnet  # noqa: E402
 
@@ -25,6 +27,7 @@ def main():
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
     H, W = 756, 1008
+    quick = '--quick' in sys.argv
     res = {}
     for regime in ('shell', 'fog'):
         st = make_state('cfgA', res=160, regime=regime)
@@ -44,7 +47,21 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MIN)
         res[regime] = {'sr_identical_all_ranks': bool(t[0].item()), 'lr_identical_all_ranks': bool(t[1].item()),
                        'maxabs': (sr - ref).abs().max().item()}
+        # a second and a third frame (the two peer frame buffers alternate): still the same pixels
+        for _ in range(2):
+            sr2, lr2 = krender.render_frame_4k_sharded(model, net, H, W, K, c2w, False, kw, test_tile=510)
+            t2 = torch.tensor([int(torch.equal(sr2, ref)), int(torch.equal(lr2['rgb_marched'], lr_ref['rgb_marched']))], device=dev)
+            if world > 1:
+                dist.all_reduce(t2, op=dist.ReduceOp.MIN)
+            res[regime]['sr_identical_all_ranks'] &= bool(t2[0].item())
+            res[regime]['lr_identical_all_ranks'] &= bool(t2[1].item())
+        frame = list(model.__dict__['_k4_cyclic_frames'].values())[0]
+        res['exchange'] = {'marcher': 'peer_stores' if frame.peers is not None else 'all_gather',
+                           'decoder': 'peer_stores' if any(v is not None for v in net.__dict__.get('_k4_peer_frames', {}).values()) else 'all_gather',
+                           'peer_error': krender_dist.PeerBuffers.last_error}
         model.mlp_mode = 'auto'
+        if quick:
+            continue
         for _ in range(2):
             krender.render_frame_4k_sharded(model, net, H, W, K, c2w, False, kw, test_tile=510)
         torch.cuda.synchronize()
@@ -64,12 +81,11 @@ def main():
         x = lr['rgb_marched'].view(H, W, 3).permute(2, 0, 1).unsqueeze(0).contiguous()
         cond = lr['depth'].view(1, H, W).contiguous()
         from k4nerf import dvgo as kdvgo
-        frame = list(model.__dict__['_k4_cyclic_frames'].values())[0]
         kw2 = dict(kw); kw2['render_depth'] = True
         make = lambda rows: tuple(t.view(-1, 3) for t in kdvgo.get_rays_of_a_view(H, W, K, c2w, False, False, False, False, rows=rows, device=dev))
         fn = lambda ro, rd, vd, hw, out: model.render_rays(ro, rd, vd, kw2, image_hw=hw, out=out)
         phases = {'march_gather': lambda: frame.render(make, fn),
-                  'march_only': lambda: (frame.k > 0) and fn(*make(frame.rows), (frame.k, W), frame.out),
+                  'march_only': lambda: (frame.k > 0) and fn(*make(frame.rows), (frame.k, W), frame.target()),
                   'decode_gather': lambda: net.tile_process_sharded(x, cond, tile_size=510)}
         for name, f in phases.items():
             f(); torch.cuda.synchronize()
