@@ -285,3 +285,24 @@ class SFTNet(nn.Module):
                 if k in cur and cur[k].size() != load_net[k].size():
                     load_net[k + '.ignore'] = load_net.pop(k)
         self.load_state_dict(load_net, strict=strict)
+
+    def save_network(self, save_root, net_label, current_iter, param_key='params'):
+        """lib/sr_esrnet.py:589-622: ``<save_root>/<net_label>_<iter|latest>.pth`` holding ``{param_key: state_dict}`` with
+        CPU tensors and any 'module.' prefix dropped -- the file ``load_network`` (and the reference's) reads back.  Like
+        the reference, a failing write is retried three times and then reported, not raised."""
+        import os
+        import time
+        name = 'latest' if current_iter == -1 else current_iter
+        save_path = os.path.join(save_root, f'{net_label}_{name}.pth')
+        state = {}
+        for key, param in self.state_dict().items():
+            state[key[7:] if key.startswith('module.') else key] = param.detach().cpu()
+        for attempt in range(3):
+            try:
+                torch.save({param_key: state}, save_path)
+                return save_path
+            except Exception as e:       # noqa: BLE001 -- the reference swallows every error here
+                print(f'Save model error: {e}, remaining retry times: {2 - attempt}')
+                time.sleep(1)
+        print(f'Still cannot save {save_path}. Just ignore it.')
+        return None

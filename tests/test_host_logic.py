@@ -145,3 +145,18 @@ def test_masked_adam_argument_validation_and_training_modules_import():
     with pytest.raises(RuntimeError, match='CUDA'):
         adam_upd_cuda.adam_upd(torch.zeros(4), torch.zeros(4), torch.zeros(4), torch.zeros(4), 1, 0.9, 0.99, 0.1, 1e-8)
     assert len(render_utils_cuda.__doc__) > 0
+
+
+def test_sftnet_save_network_round_trips_through_load_network(tmp_path):
+    """lib/sr_esrnet.py:589-622 / :529-554: '<label>_<iter>.pth' with {'params': state_dict} on the CPU, -1 -> 'latest'."""
+    torch.manual_seed(7)
+    a = k4nerf.SFTNet(3, 4, 64, 1, 32, 1)
+    path = a.save_network(str(tmp_path), 'net_sr', -1)
+    assert path == os.path.join(str(tmp_path), 'net_sr_latest.pth') and os.path.exists(path)
+    blob = torch.load(path, weights_only=False)
+    assert list(blob) == ['params'] and all(not v.is_cuda for v in blob['params'].values())
+    b = k4nerf.SFTNet(3, 4, 64, 1, 32, 1)
+    b.load_network(path, 'cpu', strict=True, param_key='params')
+    for (ka, va), (kb, vb) in zip(a.state_dict().items(), b.state_dict().items()):
+        assert ka == kb and torch.equal(va, vb)
+    assert a.save_network(str(tmp_path), 'net_sr', 1500).endswith('net_sr_1500.pth')
