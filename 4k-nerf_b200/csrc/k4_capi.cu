@@ -533,6 +533,20 @@ extern "C" int k4_peer_alloc(size_t bytes, void** d_ptr) {
     *d_ptr = p;
     return K4_OK;
 }
+extern "C" int k4_peer_enable_all(void) {
+    int dev = 0, n = 0;
+    K4_CUDA_TRY(cudaGetDevice(&dev));
+    K4_CUDA_TRY(cudaGetDeviceCount(&n));
+    for (int d = 0; d < n; ++d) {
+        if (d == dev) continue;
+        int can = 0;
+        if (cudaDeviceCanAccessPeer(&can, dev, d) != cudaSuccess || !can) { cudaGetLastError(); continue; }
+        cudaError_t e = cudaDeviceEnablePeerAccess(d, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { k4_set_cuda_error(e, "cudaDeviceEnablePeerAccess"); cudaGetLastError(); return K4_ERR_CUDA; }
+        cudaGetLastError();
+    }
+    return K4_OK;
+}
 extern "C" int k4_peer_free(void* d_ptr) {
     if (!d_ptr) return K4_OK;
     K4_CUDA_TRY(cudaFree(d_ptr));

@@ -75,6 +75,7 @@ EXPORTS = {
                                  C.c_int64, C.POINTER(RenderOut), C.c_void_p, C.c_size_t, C.c_void_p]),
     'k4_render_rays_frames': (C.c_int, [C.c_void_p, C.POINTER(RenderArgs), C.c_void_p, C.c_void_p, C.c_void_p,
                                         C.c_int64, C.POINTER(FrameDst), C.POINTER(RenderOut), C.c_void_p, C.c_size_t, C.c_void_p]),
+    'k4_peer_enable_all': (C.c_int, []),
     'k4_peer_alloc': (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p)]),
     'k4_peer_free': (C.c_int, [C.c_void_p]),
     'k4_peer_export': (C.c_int, [C.c_void_p, C.c_char_p]),

@@ -144,6 +144,8 @@ class PeerBuffers:
         ok, handles = 1, []
         with torch.cuda.device(device):
             try:
+                if os.environ.get('K4_PEER_EAGER', '1') != '0':
+                    _lib.check(_lib.lib.k4_peer_enable_all(), 'k4_peer_enable_all')
                 for _ in range(count):
                     p = C.c_void_p()
                     _lib.check(_lib.lib.k4_peer_alloc(C.c_size_t(4 * self.numel), C.byref(p)), 'k4_peer_alloc')
@@ -426,6 +428,20 @@ def sr_assign(units, world_size):
     return [sorted(m) for m in mine]
 
 
+_SR_PLANS = {}
+
+
+def sr_plan(H, W, tile_size, tile_pad, world, halo):
+    """(units, assign) of :func:`sr_units` / :func:`sr_assign`, computed once per geometry: the balancing search is a few
+    milliseconds of Python at 8 ranks -- as long as the whole 8-GPU frame -- and must not run per frame."""
+    key = (int(H), int(W), int(tile_size), int(tile_pad), int(world), int(halo))
+    plan = _SR_PLANS.get(key)
+    if plan is None:
+        units = sr_units(*key)
+        plan = _SR_PLANS[key] = (units, sr_assign(units, key[4]))
+    return plan
+
+
 def sr_decode_sharded(net_fn, img, cond, tile_size, tile_pad=10, scale=4, halo=80, group=None, net_units_fn=None,
                       peers=None):
     """x`scale` decode of ``img [1,C,H,W]`` / ``cond [1,H,W]`` (full frame on every rank) with the units
@@ -442,9 +458,8 @@ def sr_decode_sharded(net_fn, img, cond, tile_size, tile_pad=10, scale=4, halo=8
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     _, C, H, W = img.shape
     s = scale
-    units = sr_units(H, W, tile_size, tile_pad, world, halo)
+    units, assign = sr_plan(H, W, tile_size, tile_pad, world, halo)
     size = lambda u: C * (u['dst'][1] - u['dst'][0]) * (u['dst'][3] - u['dst'][2]) * s * s
-    assign = sr_assign(units, world)
     if peers is not None and net_units_fn is not None and world > 1:
         par = peers.__dict__.setdefault('_step', 0) & 1
         peers._step += 1

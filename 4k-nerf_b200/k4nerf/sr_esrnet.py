@@ -97,8 +97,8 @@ class SFTNet(nn.Module):
         return cs
 
     def _get_net(self):
-        params = [t for c in self._ordered_convs() for t in (c.weight, c.bias)]
-        fp = tuple((t.data_ptr(), t._version) for t in params)
+        params = [t for c in self._ordered_convs() for t in (c.weight, c.bias)]     # live Parameters: replaced ones are seen
+        fp = tuple([(t.data_ptr(), t._version) for t in params])
         h = getattr(self, '_k4_net', None)
         if h is not None and h.fingerprint == fp:
             return h

@@ -189,6 +189,7 @@ K4_API int k4_render_rays_frames(const k4_scene* scene, const k4_render_args* ar
  * (pool / async allocations cannot be exported), k4_peer_export fills the 64-byte CUDA IPC handle to send to the other
  * ranks (any transport: torch.distributed.all_gather_object), k4_peer_open maps another PROCESS's allocation into the
  * current device's address space with peer access enabled, k4_peer_close unmaps it. */
+K4_API int k4_peer_enable_all(void);                 /* peer access from the current device to every device that allows it */
 K4_API int k4_peer_alloc(size_t bytes, void** d_ptr);
 K4_API int k4_peer_free(void* d_ptr);
 K4_API int k4_peer_export(void* d_ptr, unsigned char handle[64]);

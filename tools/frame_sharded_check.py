@@ -29,7 +29,8 @@ def main():
     H, W = 756, 1008
     quick = '--quick' in sys.argv
     res = {}
-    for regime in ('shell', 'fog'):
+    order = ('fog', 'shell') if '--fog-first' in sys.argv else ('shell', 'fog')
+    for regime in order:
         st = make_state('cfgA', res=160, regime=regime)
         model = model_from_state(st, dev)
         net = k4nerf.SFTNet(3, 4, 64, 5, 32, 1)
@@ -68,15 +69,19 @@ def main():
         if world > 1:
             dist.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        import time
         e0.record()
+        h0 = time.perf_counter()
         for _ in range(5):
             krender.render_frame_4k_sharded(model, net, H, W, K, c2w, False, kw, test_tile=510)
+        host_ms = (time.perf_counter() - h0) * 1e3 / 5          # time to ENQUEUE a frame (nothing waits for the GPU here)
         e1.record()
         torch.cuda.synchronize()
-        tm = torch.tensor([e0.elapsed_time(e1) / 5], device=dev)
+        tm = torch.tensor([e0.elapsed_time(e1) / 5, host_ms], device=dev)
         if world > 1:
             dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-        res[regime]['ms_per_frame'] = tm.item()
+        res[regime]['ms_per_frame'] = tm[0].item()
+        res[regime]['host_enqueue_ms_per_frame'] = round(tm[1].item(), 3)
         # phase breakdown (max over ranks): the marcher + its all-gather, and the decoder + its all-gather, timed apart
         x = lr['rgb_marched'].view(H, W, 3).permute(2, 0, 1).unsqueeze(0).contiguous()
         cond = lr['depth'].view(1, H, W).contiguous()
@@ -87,6 +92,31 @@ def main():
         phases = {'march_gather': lambda: frame.render(make, fn),
                   'march_only': lambda: (frame.k > 0) and fn(*make(frame.rows), (frame.k, W), frame.target()),
                   'decode_gather': lambda: net.tile_process_sharded(x, cond, tile_size=510)}
+        if world > 1 and '--peer-breakdown' in sys.argv and net.__dict__.get('_k4_peer_frames'):
+            # where does a peer-mode decode spend its time: the unit with / without the stores into the other ranks' frames,
+            # with / without the barrier (timing only: without the stores the other ranks' frames are incomplete)
+            pb = krender_dist.PeerBuffers
+            real_sync, real_units = pb.sync, net.run_units
+            dec = phases['decode_gather']
+            def no_sync(): pb.sync = lambda self: None
+            def with_sync(): pb.sync = real_sync
+            def local_only(): net.run_units = lambda jobs, streams=2: real_units([j[:4] for j in jobs], streams)
+            def with_peers(): net.__dict__.pop('run_units', None)
+            variants = {'decode_peer_sync': (with_peers, with_sync), 'decode_peer_nosync': (with_peers, no_sync),
+                        'decode_local_nosync': (local_only, no_sync), 'decode_local_sync': (local_only, with_sync)}
+            for name, (a, b) in variants.items():
+                a(); b()
+                dec(); torch.cuda.synchronize(); dist.barrier()
+                e0.record()
+                for _ in range(5):
+                    dec()
+                e1.record()
+                torch.cuda.synchronize()
+                mine = torch.tensor([e0.elapsed_time(e1) / 5], device=dev)
+                allr = [torch.zeros_like(mine) for _ in range(world)]
+                dist.all_gather(allr, mine)
+                res[regime][name + '_ms_by_rank'] = [round(t.item(), 3) for t in allr]
+            with_peers(); with_sync()
         for name, f in phases.items():
             f(); torch.cuda.synchronize()
             if world > 1:
