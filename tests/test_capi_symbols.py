@@ -41,3 +41,20 @@ def test_no_oracle_import_in_product():
             if f.endswith(('.py', '.cu', '.cuh', '.h')):
                 src = open(os.path.join(dp, f)).read()
                 assert 'import oracle' not in src and 'from oracle' not in src, f
+
+
+def test_multi_gpu_entry_points_validate_arguments_without_a_gpu():
+    """k4_render_rays_frames / k4_srnet_forward_roi_peers / k4_peer_*: argument errors are reported as status codes before
+    any CUDA call (no compute here -- there is no GPU in the CPU test environment)."""
+    from k4nerf import _lib
+    C = ctypes
+    lib = _lib.lib
+    assert lib.k4_render_rays_frames(None, None, None, None, None, 0, None, None, None, 0, None) == -1       # K4_ERR_INVALID_ARG
+    assert lib.k4_srnet_forward_roi_peers(None, None, None, 8, 8, 0, 8, 0, 8, None, 0, 0, 0, None, None, 0, None) == -1
+    p = C.c_void_p()
+    assert lib.k4_peer_alloc(0, C.byref(p)) == -1 and p.value is None
+    assert lib.k4_peer_export(None, C.create_string_buffer(64)) == -1
+    assert lib.k4_peer_open(None, C.byref(p)) == -1
+    assert lib.k4_peer_free(None) == 0 and lib.k4_peer_close(None) == 0
+    d = _lib.FrameDst()
+    assert C.sizeof(d) == 4 * 4 + 8 + 8 * _lib.K4_MAX_PEERS                 # the header's k4_frame_dst, field for field

@@ -176,3 +176,34 @@ def test_sr_units_cover_and_halo():
             y0, y1, x0, x1 = u['dst']
             out[:, :, 4 * y0:4 * y1, 4 * x0:4 * x1] = o[:, :, 4 * ky:4 * (ky + y1 - y0), 4 * kx:4 * (kx + x1 - x0)]
         assert torch.equal(out, ref), world
+
+
+def test_sr_plan_is_the_cached_units_and_assignment():
+    from k4nerf import dist as kdist
+    for world in (1, 2, 3, 4, 8):
+        units, assign = kdist.sr_plan(756, 1008, 510, 10, world, 80)
+        assert units == kdist.sr_units(756, 1008, 510, 10, world, 80)
+        assert assign == kdist.sr_assign(units, world)
+        again = kdist.sr_plan(756, 1008, 510, 10, world, 80)
+        assert again[0] is units and again[1] is assign                  # no search on the per-frame path
+
+
+def test_peer_buffers_fall_back_without_cuda_and_frame_target_layout():
+    """PeerBuffers.create is collective and answers None off the GPUs of one node (here: no process group, CPU) -- the
+    callers then take the all-gather path the gloo tests above exercise; FrameTarget fills k4_frame_dst."""
+    from k4nerf import dist as kdist
+    assert kdist.PeerBuffers.create(1024, 'cpu') is None
+    t = kdist.FrameTarget([0x1000, 0x2000, 0x3000], rank=1, world=3, W=72, n_full=3 * 24 * 72)
+    d = t.frame_dst
+    assert (d.n_dst, d.rank, d.world, d.frame_w, d.n_full) == (3, 1, 3, 72, 3 * 24 * 72)
+    assert [d.d_frame[i] for i in range(3)] == [0x1000, 0x2000, 0x3000] and d.d_frame[3] is None
+    H, W, world = 50, 72, 3
+    n_full = world * kdist.cyclic_pad_rows(H, world) * W
+    full = torch.arange(5 * n_full, dtype=torch.float32)
+    v = kdist.frame_views(full, H, W, n_full)
+    assert v['rgb_marched'].shape == (H * W, 3) and v['rgb_marched'][1, 0] == 3.0
+    assert v['depth'][0] == 3 * n_full and v['alphainv_last'][H * W - 1] == 4 * n_full + H * W - 1
+    # the kernel's row map (k4_store_ray): local row r of rank q is image row ((r // 8) * world + q) * 8 + r % 8
+    for q in range(world):
+        rows = kdist.cyclic_rows(H, q, world).tolist()
+        assert rows == [((r // 8) * world + q) * 8 + r % 8 for r in range(len(rows))]
