@@ -9,6 +9,7 @@ import numpy as np
 import torch
 
 from . import dvgo
+from .utils import to8b
 
 
 @torch.no_grad()
@@ -48,19 +49,51 @@ def _post(rgbs, depths, bgmaps, render_video_flipy, render_video_rot90):
             bgmaps[i] = np.rot90(bgmaps[i], k=render_video_rot90, axes=(0, 1))
 
 
+def _write_png(filename, rgb8):
+    """imageio.imwrite of the reference (run.py:165, run_sr.py:175), with the writers this environment may have instead."""
+    try:
+        import imageio
+        imageio.imwrite(filename, rgb8)
+        return
+    except ImportError:
+        pass
+    try:
+        from PIL import Image
+        Image.fromarray(rgb8).save(filename)
+        return
+    except ImportError:
+        pass
+    import cv2
+    cv2.imwrite(filename, rgb8[..., ::-1])
+
+
+def _dump(rgbs, savedir, dump_images, global_step):
+    """run.py:161-165 / run_sr.py:171-175: ``e<global_step>_<index>.png`` of the (flipped / rotated) 8-bit frames."""
+    if savedir is None or not dump_images:
+        return
+    import os
+    for i, rgb in enumerate(rgbs):
+        _write_png(os.path.join(savedir, 'e{}_{:03d}.png'.format(global_step, i)), to8b(np.ascontiguousarray(rgb)))
+
+
 @torch.no_grad()
 def render_viewpoints(model, render_poses, HW, Ks, ndc, render_kwargs,
                       gt_imgs=None, savedir=None, dump_images=False,
                       render_factor=0, render_video_flipy=False, render_video_rot90=0,
-                      eval_ssim=False, eval_lpips_alex=False, eval_lpips_vgg=False,
-                      flip_x=None, flip_y=None):
-    """run.py:66-171 contract: returns ``(rgbs, depths, bgmaps, psnrs, ssims, lpips_vgg)``.
+                      eval_ssim=False, eval_lpips_alex=False, eval_lpips_vgg=False, global_step=0,
+                      arr_index=None, img_enc=None, flip_x=None, flip_y=None):
+    """run.py:66-171 contract: returns ``(rgbs, depths, bgmaps, psnrs, ssims, lpips_vgg)``; ``savedir`` +
+    ``dump_images`` write ``e<global_step>_<i>.png`` like the reference.
 
     The reference reads ``cfg.data.flip_x/flip_y`` from a module global (run.py:96); here they come
-    from ``render_kwargs`` unless passed explicitly."""
+    from ``render_kwargs`` unless passed explicitly.  The reference's defaults evaluate SSIM and LPIPS-VGG when ground
+    truth is given; those metrics (``lib/utils.py`` + the ``lpips`` package) are outside the rendering path and are not
+    provided: asking for them raises."""
     assert len(render_poses) == len(HW) and len(HW) == len(Ks)
     if eval_lpips_alex or eval_lpips_vgg or eval_ssim:
         raise NotImplementedError('SSIM/LPIPS evaluation is outside the rendering hot path')
+    if arr_index is not None or img_enc is not None:
+        raise NotImplementedError('img_enc conditioning needs lib/img_encoder, which the reference does not ship')
     flip_x = render_kwargs.get('flip_x', False) if flip_x is None else flip_x
     flip_y = render_kwargs.get('flip_y', False) if flip_y is None else flip_y
     frames = _render_frames(model, render_poses, HW, Ks, ndc, render_kwargs, render_factor, flip_x, flip_y)
@@ -73,6 +106,7 @@ def render_viewpoints(model, render_poses, HW, Ks, ndc, render_kwargs,
         if gt_imgs is not None and render_factor == 0:
             psnrs.append(-10. * np.log10(np.mean(np.square(rgb - gt_imgs[i]))))
     _post(rgbs, depths, bgmaps, render_video_flipy, render_video_rot90)
+    _dump(rgbs, savedir, dump_images, global_step)
     return np.array(rgbs), np.array(depths), np.array(bgmaps), psnrs, [], []
 
 
@@ -101,6 +135,7 @@ def render_viewpoints_sr(model, render_poses, HW, Ks, ndc, render_kwargs,
         if gt_imgs is not None and render_factor == 0:
             psnrs.append(-10. * np.log10(np.mean(np.square(rgb - gt_imgs[i]))))
     _post(rgbs, depths, bgmaps, render_video_flipy, render_video_rot90)
+    _dump(rgbs, savedir, dump_images, global_step)
     return np.array(rgbs), np.array(depths), np.array(bgmaps), psnrs, viewdirs_all, np.array(rgb_features)
 
 

@@ -160,3 +160,18 @@ def test_sftnet_save_network_round_trips_through_load_network(tmp_path):
     for (ka, va), (kb, vb) in zip(a.state_dict().items(), b.state_dict().items()):
         assert ka == kb and torch.equal(va, vb)
     assert a.save_network(str(tmp_path), 'net_sr', 1500).endswith('net_sr_1500.pth')
+
+
+def test_render_viewpoints_dump_images_writes_the_reference_file_names(tmp_path):
+    """run.py:161-165 / run_sr.py:171-175: e<global_step>_<index>.png of the 8-bit frames (after the video flip / rot90)."""
+    import numpy as np
+    from k4nerf import render
+    rgbs = [np.random.RandomState(i).rand(6, 8, 3).astype(np.float32) * 1.2 - 0.1 for i in range(2)]
+    render._dump(rgbs, str(tmp_path), True, 1500)
+    assert sorted(os.listdir(tmp_path)) == ['e1500_000.png', 'e1500_001.png']
+    from PIL import Image
+    got = np.array(Image.open(os.path.join(tmp_path, 'e1500_001.png')))
+    assert np.array_equal(got, render.to8b(rgbs[1]))
+    render._dump(rgbs, None, True, 0)                  # no directory / not asked for: nothing happens
+    render._dump(rgbs, str(tmp_path), False, 0)
+    assert len(os.listdir(tmp_path)) == 2
