@@ -9,7 +9,7 @@ import numpy as np
 import torch
 
 from . import dvgo
-from .utils import to8b
+from .utils import rgb_ssim, to8b
 
 
 @torch.no_grad()
@@ -67,6 +67,14 @@ def _write_png(filename, rgb8):
     cv2.imwrite(filename, rgb8[..., ::-1])
 
 
+def _report(psnrs, ssims):
+    """run.py:141-145 / run_sr.py:153-157."""
+    if len(psnrs):
+        print('Testing psnr', np.mean(psnrs), '(avg)')
+        if len(ssims):
+            print('Testing ssim', np.mean(ssims), '(avg)')
+
+
 def _dump(rgbs, savedir, dump_images, global_step):
     """run.py:161-165 / run_sr.py:171-175: ``e<global_step>_<index>.png`` of the (flipped / rotated) 8-bit frames."""
     if savedir is None or not dump_images:
@@ -87,17 +95,17 @@ def render_viewpoints(model, render_poses, HW, Ks, ndc, render_kwargs,
 
     The reference reads ``cfg.data.flip_x/flip_y`` from a module global (run.py:96); here they come
     from ``render_kwargs`` unless passed explicitly.  The reference's defaults evaluate SSIM and LPIPS-VGG when ground
-    truth is given; those metrics (``lib/utils.py`` + the ``lpips`` package) are outside the rendering path and are not
-    provided: asking for them raises."""
+    truth is given (here both default to off): ``eval_ssim`` is provided (``utils.rgb_ssim``, CPU), LPIPS needs the
+    ``lpips`` package and its pretrained VGG / AlexNet weights and raises."""
     assert len(render_poses) == len(HW) and len(HW) == len(Ks)
-    if eval_lpips_alex or eval_lpips_vgg or eval_ssim:
-        raise NotImplementedError('SSIM/LPIPS evaluation is outside the rendering hot path')
+    if eval_lpips_alex or eval_lpips_vgg:
+        raise NotImplementedError('LPIPS evaluation needs the lpips package and its pretrained weights')
     if arr_index is not None or img_enc is not None:
         raise NotImplementedError('img_enc conditioning needs lib/img_encoder, which the reference does not ship')
     flip_x = render_kwargs.get('flip_x', False) if flip_x is None else flip_x
     flip_y = render_kwargs.get('flip_y', False) if flip_y is None else flip_y
     frames = _render_frames(model, render_poses, HW, Ks, ndc, render_kwargs, render_factor, flip_x, flip_y)
-    rgbs, depths, bgmaps, psnrs = [], [], [], []
+    rgbs, depths, bgmaps, psnrs, ssims = [], [], [], [], []
     for i, f in enumerate(frames):
         rgb = f['rgb_marched'].clamp(0, 1).cpu().numpy()
         rgbs.append(rgb)
@@ -105,9 +113,12 @@ def render_viewpoints(model, render_poses, HW, Ks, ndc, render_kwargs,
         bgmaps.append(f['alphainv_last'].cpu().numpy())
         if gt_imgs is not None and render_factor == 0:
             psnrs.append(-10. * np.log10(np.mean(np.square(rgb - gt_imgs[i]))))
+            if eval_ssim:
+                ssims.append(rgb_ssim(rgb, gt_imgs[i], max_val=1))          # run.py:134-135
+    _report(psnrs, ssims)
     _post(rgbs, depths, bgmaps, render_video_flipy, render_video_rot90)
     _dump(rgbs, savedir, dump_images, global_step)
-    return np.array(rgbs), np.array(depths), np.array(bgmaps), psnrs, [], []
+    return np.array(rgbs), np.array(depths), np.array(bgmaps), psnrs, ssims, []
 
 
 @torch.no_grad()
@@ -124,7 +135,9 @@ def render_viewpoints_sr(model, render_poses, HW, Ks, ndc, render_kwargs,
     flip_x = render_kwargs.get('flip_x', False) if flip_x is None else flip_x
     flip_y = render_kwargs.get('flip_y', False) if flip_y is None else flip_y
     frames = _render_frames(model, render_poses, HW, Ks, ndc, render_kwargs, render_factor, flip_x, flip_y)
-    rgbs, rgb_features, depths, bgmaps, psnrs, viewdirs_all = [], [], [], [], [], []
+    if eval_lpips_alex or eval_lpips_vgg:
+        raise NotImplementedError('LPIPS evaluation needs the lpips package and its pretrained weights')
+    rgbs, rgb_features, depths, bgmaps, psnrs, ssims, viewdirs_all = [], [], [], [], [], [], []
     for i, f in enumerate(frames):
         rgb = f['rgb_marched'].clamp(0, 1).cpu().numpy()
         rgbs.append(rgb)
@@ -134,6 +147,9 @@ def render_viewpoints_sr(model, render_poses, HW, Ks, ndc, render_kwargs,
         viewdirs_all.append(f['viewdirs'])
         if gt_imgs is not None and render_factor == 0:
             psnrs.append(-10. * np.log10(np.mean(np.square(rgb - gt_imgs[i]))))
+            if eval_ssim:
+                ssims.append(rgb_ssim(rgb, gt_imgs[i], max_val=1))          # run_sr.py:146-147 (printed, not returned)
+    _report(psnrs, ssims)
     _post(rgbs, depths, bgmaps, render_video_flipy, render_video_rot90)
     _dump(rgbs, savedir, dump_images, global_step)
     return np.array(rgbs), np.array(depths), np.array(bgmaps), psnrs, viewdirs_all, np.array(rgb_features)

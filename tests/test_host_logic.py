@@ -175,3 +175,31 @@ def test_render_viewpoints_dump_images_writes_the_reference_file_names(tmp_path)
     render._dump(rgbs, None, True, 0)                  # no directory / not asked for: nothing happens
     render._dump(rgbs, str(tmp_path), False, 0)
     assert len(os.listdir(tmp_path)) == 2
+
+
+def test_rgb_ssim_matches_the_windowed_definition():
+    """utils.rgb_ssim (lib/utils.py:88-134) against a direct evaluation of the definition: 11x11 Gaussian window
+    (sigma 1.5) at every 'valid' position, per channel."""
+    import numpy as np
+    from k4nerf.utils import rgb_ssim
+    rs = np.random.RandomState(0)
+    a = rs.rand(20, 23, 3)
+    b = np.clip(a + 0.1 * rs.randn(20, 23, 3), 0, 1)
+    assert abs(rgb_ssim(a, a, 1) - 1.0) < 1e-12
+    t = np.arange(11) - 5
+    g = np.exp(-0.5 * (t / 1.5) ** 2); g /= g.sum()
+    w2 = np.outer(g, g)
+    c1, c2 = 0.01 ** 2, 0.03 ** 2
+    vals = []
+    for y in range(20 - 10):
+        for x in range(23 - 10):
+            for c in range(3):
+                p, q = a[y:y + 11, x:x + 11, c], b[y:y + 11, x:x + 11, c]
+                m0, m1 = (w2 * p).sum(), (w2 * q).sum()
+                v0 = max((w2 * p * p).sum() - m0 * m0, 0.0); v1 = max((w2 * q * q).sum() - m1 * m1, 0.0)
+                cv = (w2 * p * q).sum() - m0 * m1
+                cv = np.sign(cv) * min(np.sqrt(v0 * v1), abs(cv))
+                vals.append((2 * m0 * m1 + c1) * (2 * cv + c2) / ((m0 * m0 + m1 * m1 + c1) * (v0 + v1 + c2)))
+    got = rgb_ssim(a.astype(np.float32), b.astype(np.float32), max_val=1)
+    assert abs(got - np.mean(vals)) < 1e-6 and 0 < got < 1
+    assert rgb_ssim(a, b, 1, return_map=True).shape == (10, 13, 3)
