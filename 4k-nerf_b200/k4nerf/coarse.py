@@ -145,6 +145,30 @@ def get_rays(H, W, K, c2w, inverse_y, flip_x, flip_y, mode='center'):
     return rays_o, rays_d
 
 
+def ndc_rays(H, W, focal, near, rays_o, rays_d):
+    """Rays of a forward-facing scene in normalised device coordinates (lib/dvgo.py:557-575, the NeRF LLFF warp): origins
+    moved onto the near plane z = -near, then x, y scaled by the frustum (2 focal / W, 2 focal / H) over -z and z mapped
+    to 1 + 2 near / z; directions are the differences to the rays' images at infinity."""
+    t = -(near + rays_o[..., 2]) / rays_d[..., 2]
+    o = rays_o + t[..., None] * rays_d
+    sx, sy = -2. * focal / W, -2. * focal / H          # == -1 / (W / (2 focal)), -1 / (H / (2 focal))
+    ox, oy, oz = o[..., 0] / o[..., 2], o[..., 1] / o[..., 2], o[..., 2]
+    new_o = torch.stack([sx * ox, sy * oy, 1. + 2. * near / oz], -1)
+    new_d = torch.stack([sx * (rays_d[..., 0] / rays_d[..., 2] - ox), sy * (rays_d[..., 1] / rays_d[..., 2] - oy),
+                         -2. * near / oz], -1)
+    return new_o, new_d
+
+
+def get_rays_of_a_view_torch(H, W, K, c2w, ndc, inverse_y, flip_x, flip_y, mode='center'):
+    """lib/dvgo.py:577-582 in plain torch on c2w's device -- the sub-pixel modes the device kernel does not generate
+    ('lefttop', 'random'; 'center' works too): rays, unit view directions taken BEFORE the NDC warp, optional warp."""
+    rays_o, rays_d = get_rays(H, W, K, c2w, inverse_y=inverse_y, flip_x=flip_x, flip_y=flip_y, mode=mode)
+    viewdirs = rays_d / rays_d.norm(dim=-1, keepdim=True)
+    if ndc:
+        rays_o, rays_d = ndc_rays(H, W, float(np.asarray(K)[0][0]), 1., rays_o, rays_d)
+    return rays_o, rays_d, viewdirs
+
+
 def _views(rgb_tr, train_poses, HW, Ks, ndc, inverse_y, flip_x, flip_y):
     from .dvgo import get_rays_of_a_view
     for img, c2w, (H, W), K in zip(rgb_tr, train_poses, HW, Ks):

@@ -133,7 +133,14 @@ def get_rays_of_a_view(H, W, K, c2w, ndc, inverse_y, flip_x, flip_y, mode='cente
     ``rows`` (int32 CUDA tensor of image-row indices, not in the reference signature): only those rows are
     generated, ``[len(rows), W, 3]`` -- a rank's share of the frame in the multi-GPU driver."""
     if mode != 'center':
-        raise NotImplementedError("only mode='center' (the render path) is built")
+        # 'lefttop' / 'random' sub-pixel positions are training-data options (lib/dvgo.py:520-528): plain torch
+        from .coarse import get_rays_of_a_view_torch
+        if rows is not None:
+            raise NotImplementedError("rows= (multi-GPU frame sharding) is built for mode='center' only")
+        c2w_t = torch.as_tensor(c2w, dtype=torch.float32)
+        if device is not None:
+            c2w_t = c2w_t.to(device)
+        return get_rays_of_a_view_torch(H, W, K, c2w_t, ndc, inverse_y, flip_x, flip_y, mode=mode)
     import ctypes as C
     c2w = torch.as_tensor(c2w, dtype=torch.float32)
     if device is not None:

@@ -203,3 +203,26 @@ def test_rgb_ssim_matches_the_windowed_definition():
     got = rgb_ssim(a.astype(np.float32), b.astype(np.float32), max_val=1)
     assert abs(got - np.mean(vals)) < 1e-6 and 0 < got < 1
     assert rgb_ssim(a, b, 1, return_map=True).shape == (10, 13, 3)
+
+
+@pytest.mark.parametrize('ndc', [False, True])
+@pytest.mark.parametrize('mode', ['lefttop', 'center'])
+def test_get_rays_of_a_view_torch_modes_match_the_oracle(ndc, mode):
+    """lib/dvgo.py:516-582: the sub-pixel modes the device kernel does not generate run in plain torch; same values as
+    the oracle's restatement (flips, inverse_y, NDC warp; view directions taken before the warp)."""
+    from k4nerf import dvgo, coarse
+    from oracle import pipeline as opipe, scenes
+    H, W = 13, 17
+    K, c2w = scenes.llff_camera(H, W, (0.05, -0.03, 0.0)) if ndc else scenes.blender_camera(H, W)
+    for inv_y, fx, fy in ((False, False, False), (True, True, False), (False, False, True)):
+        ref = opipe.get_rays_of_a_view(H, W, K, c2w, ndc, inv_y, fx, fy, mode=mode)
+        got = coarse.get_rays_of_a_view_torch(H, W, K, c2w, ndc, inv_y, fx, fy, mode=mode)
+        for a, b in zip(got, ref):
+            assert a.shape == (H, W, 3) and torch.allclose(a, b, rtol=1e-6, atol=1e-6)
+    if mode != 'center':        # the public entry point routes non-centre modes to the torch path (no GPU needed)
+        got = dvgo.get_rays_of_a_view(H, W, K, c2w, ndc, False, False, False, mode=mode)
+        ref = opipe.get_rays_of_a_view(H, W, K, c2w, ndc, False, False, False, mode=mode)
+        assert all(torch.allclose(a, b, rtol=1e-6, atol=1e-6) for a, b in zip(got, ref))
+    r = dvgo.get_rays_of_a_view(H, W, K, c2w, ndc, False, False, False, mode='random')
+    lo = opipe.get_rays_of_a_view(H, W, K, c2w, False, False, False, False, mode='lefttop')
+    assert r[0].shape == (H, W, 3) and torch.isfinite(r[1]).all() and lo[0].shape == (H, W, 3)
