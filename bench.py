@@ -625,17 +625,18 @@ def secondary_sharded(model, kw, dev, world):
         net = net.to(dev)
         K, c2w = scenes.blender_camera(HLR, WLR, *POSES[0])
         run = lambda: krender.render_frame_4k_sharded(model, net, HLR, WLR, K, c2w, False, kw, test_tile=510)
-        for _ in range(2):
+        n_warm, n_timed = 4, 10          # the frame is ~6-15 ms: three frames after two warm-ups measured the clock ramp
+        for _ in range(n_warm):
             run()
         torch.cuda.synchronize()
         dist.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for _ in range(3):
+        for _ in range(n_timed):
             sr, _ = run()
         e1.record()
         torch.cuda.synchronize()
-        t = torch.tensor([e0.elapsed_time(e1) / 3], device=dev)
+        t = torch.tensor([e0.elapsed_time(e1) / n_timed], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         out['configs[4]_full_frame_1008x756_to_4032x3024_sharded'] = {
             'ms_per_frame': t.item(), 'frames_per_s': 1e3 / t.item(), 'n_gpus': world,
